@@ -1,0 +1,211 @@
+/*
+ * b2d.h — C ABI of libb2d: the B200-native DDP gradient-sync data path.
+ *
+ * This is the drop-in boundary of the repo.  The
+ * library replaces, for one 8xB200 NVSwitch box, the collectives that the
+ * reference's strategies reach through torch DDP / FairScale:
+ *
+ *   reference seam                                   replaced by
+ *   ------------------------------------------------ ---------------------------
+ *   ray_lightning/ray_ddp.py:112-116  (**ddp_kwargs  b2d_allreduce_bucket()
+ *     -> DistributedDataParallel -> c10d::Reducer      (one call per DDP bucket,
+ *     -> ncclAllReduce per bucket; with                 fp32->bf16 cast, 1/W scale,
+ *     bf16_compress_hook: cast, div, allreduce, copy)    P2P reduce, fp32 write-back
+ *                                                       fused in ONE kernel)
+ *   ray_lightning/ray_ddp.py:192-196  (process group  b2d_ctx_create/export/import
+ *     init; peers become addressable)                   /finalize (peer mapping)
+ *   ray_lightning/ray_ddp_sharded.py:12-13            b2d_sharded_step()
+ *     (FairScale ShardedDataParallel reduce-to-owner    (reduce-scatter to owner +
+ *      + OSS.step + OSS._broadcast_params)               partitioned Adam + param
+ *                                                       all-gather, one kernel),
+ *                                                     b2d_reduce_scatter(),
+ *                                                     b2d_allgather()
+ *   ray_lightning/launchers/ray_launcher.py:177-219   (precondition: every worker
+ *     (_share_cuda_visible_devices)                    sees every GPU of its node)
+ *
+ * Conventions
+ *   - plain C, no torch / pybind types; loadable with ctypes / cgo / JNI.
+ *   - every entry point returns 0 on success, a negative b2d_status otherwise;
+ *     never throws; b2d_last_error() gives the message (per ctx, or the
+ *     thread-local creation error when ctx == NULL).
+ *   - data-path entry points only ENQUEUE work on `comm_stream` (after making
+ *     it wait for `wait_stream`); they never synchronise the device.
+ *   - streams are passed as `void*` holding a cudaStream_t (0 = legacy default).
+ *   - the caller owns every tensor pointer; the library owns the symmetric
+ *     arena, the signal pads, the peer mappings and the multicast object.
+ *   - all ranks of a job must issue the same sequence of data-path calls with
+ *     the same sizes (DDP guarantees this for buckets: reducer.hpp:282,524).
+ *   - a peer that never arrives makes the kernel trap after `timeout_ms`
+ *     (b2d_ctx_set_timeout); the next CUDA call then returns a sticky error.
+ */
+#ifndef B2D_H_
+#define B2D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_VERSION 100          /* 0.1.0 */
+#define B2D_MAX_WORLD 8          /* one NVSwitch domain: 8 x B200 */
+#define B2D_MAX_BLOCKS 296       /* 2 x 148 SMs */
+#define B2D_HANDLE_BYTES 256     /* size of the blob b2d_ctx_export() writes */
+
+typedef struct b2d_ctx b2d_ctx;
+
+typedef enum b2d_status {
+  B2D_OK = 0,
+  B2D_ERR_INVALID = -1,      /* bad argument */
+  B2D_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed */
+  B2D_ERR_STATE = -3,        /* call made in the wrong phase (e.g. before finalize) */
+  B2D_ERR_NOMEM = -4,        /* symmetric arena exhausted */
+  B2D_ERR_UNSUPPORTED = -5,  /* feature not available on this box (e.g. multicast) */
+  B2D_ERR_PEER = -6          /* peer mapping failed / peer timeout recorded */
+} b2d_status;
+
+/* wire formats of the exchange */
+typedef enum b2d_wire {
+  B2D_WIRE_FP32 = 0,  /* peers exchange fp32: matches DDP's default allreduce
+                         (default_comm_hooks.hpp:36-51): out = sum_r g_r * scale */
+  B2D_WIRE_BF16 = 1   /* peers exchange bf16: matches bf16_compress_hook
+                         (default_hooks.py:57-93,116-134):
+                         c_r = bf16(bf16(g_r) * scale); s = bf16(sum_r c_r); out = fp32(s) */
+} b2d_wire;
+
+typedef enum b2d_algo {
+  B2D_ALGO_AUTO = 0,
+  B2D_ALGO_ONE_SHOT = 1,   /* every rank reads every peer's whole staged bucket */
+  B2D_ALGO_TWO_SHOT = 2,   /* reduce-scatter of 1/W slices + all-gather, both by peer reads */
+  B2D_ALGO_NVLS = 3        /* multimem.ld_reduce / multimem.st through the NVSwitch */
+} b2d_algo;
+
+/* b2d_ctx_create flags */
+#define B2D_FLAG_MEM_LEGACY_IPC 0x0u /* arena = cudaMalloc, shared by cudaIpc handles (default) */
+#define B2D_FLAG_MEM_VMM        0x1u /* arena = cuMemCreate (POSIX fd handles); needed for NVLS */
+#define B2D_FLAG_TIMING         0x2u /* record a CUDA-event pair around every kernel launch */
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+int b2d_version(void);
+
+/* Create the per-rank context on CUDA device `device` (index inside the process's
+ * CUDA_VISIBLE_DEVICES, i.e. RayStrategy.root_device.index, ray_ddp.py:259-304) and
+ * allocate its symmetric arena (`arena_bytes`, rounded up to 2 MiB) and signal pad.
+ * Several contexts may live in one process (also on the same device: "loopback"
+ * ranks used by the single-GPU tests). */
+int b2d_ctx_create(int rank, int world, int device, size_t arena_bytes,
+                   unsigned flags, b2d_ctx** out);
+
+/* Write this rank's B2D_HANDLE_BYTES-byte handle blob.  The blob travels to the peers
+ * over whatever control plane the host already has (torch.distributed
+ * all_gather_object, the Ray object store, ...).  For B2D_FLAG_MEM_VMM contexts the
+ * blob additionally names a POSIX file descriptor (b2d_ctx_export_fd) that the host
+ * must pass with SCM_RIGHTS and patch in with b2d_handle_set_fd() on the receiver. */
+int b2d_ctx_export(b2d_ctx* ctx, void* handle_buf, size_t* len);
+int b2d_ctx_export_fd(b2d_ctx* ctx, int* fd_out);
+int b2d_handle_set_fd(void* handle_buf, size_t len, int fd);
+
+/* Map peer `peer`'s arena + signal pad into this process / device. */
+int b2d_ctx_import(b2d_ctx* ctx, int peer, const void* handle_buf, size_t len);
+
+/* After all world-1 imports: upload the peer pointer tables.  Host must run a
+ * control-plane barrier between the last b2d_ctx_finalize() and the first data call. */
+int b2d_ctx_finalize(b2d_ctx* ctx);
+
+/* NVLS (NVLink-SHARP multicast), optional: rank 0 creates the multicast object and
+ * exports its fd; every rank (rank 0 included) joins with the fd, then — after a
+ * control-plane barrier — binds its arena.  Returns B2D_ERR_UNSUPPORTED when the
+ * device or driver does not expose multicast. */
+int b2d_mc_supported(b2d_ctx* ctx, int* supported);
+int b2d_mc_create(b2d_ctx* ctx, int* fd_out);
+int b2d_mc_join(b2d_ctx* ctx, int fd);
+int b2d_mc_bind(b2d_ctx* ctx);
+
+int b2d_ctx_destroy(b2d_ctx* ctx);
+const char* b2d_last_error(b2d_ctx* ctx);
+
+/* ---- knobs ----------------------------------------------------------------------------- */
+
+int b2d_ctx_set_timeout(b2d_ctx* ctx, unsigned timeout_ms);  /* peer-flag watchdog; default 10000 */
+int b2d_ctx_set_max_ctas(b2d_ctx* ctx, int max_ctas);        /* CTAs per comm kernel; default 64 */
+int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes); /* AUTO: one-shot at or below */
+
+/* ---- data path ------------------------------------------------------------------------- */
+
+/* In-place allreduce of one DDP gradient bucket (K0/K1/K2/K3).
+ *   grad_inout : this rank's flat fp32 bucket (GradBucket.buffer(), comm.hpp:20-98), n elements
+ *   bucket_idx : GradBucket.index(); selects the arena slot (double-buffered, so no
+ *                trailing barrier is needed between consecutive steps)
+ *   scale      : 1/world for DDP averaging (applied before the wire cast)
+ * world == 1 degenerates to the cast/scale round trip (K0) with no peer access. */
+int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad_inout, size_t n,
+                         int wire, float scale, int algo,
+                         void* wait_stream, void* comm_stream);
+
+/* Hyper-parameters of the partitioned Adam (torch/optim/adam.py:347-547 semantics,
+ * non-amsgrad, non-maximize).  `step` is the 1-based step count AFTER increment. */
+typedef struct b2d_adam {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;
+  int32_t adamw;      /* 0: L2 (grad += wd*p) like torch.optim.Adam; 1: decoupled like AdamW */
+  int32_t zero_grads; /* 1: overwrite the local flat grads with 0 once they are staged */
+} b2d_adam;
+
+/* Sharded optimizer step (K4+K5+K6 fused): the flat fp32 gradient space [0, n) is cut
+ * into `world` contiguous owner shards shard_off[r] .. shard_off[r+1] (element offsets,
+ * world+1 entries, multiples of 8, parameter aligned — FairScale OSS.partition_parameters
+ * ownership).  Rank r: reduces its shard from all peers (x scale), applies Adam to
+ * params/exp_avg/exp_avg_sq of that shard, and every rank then gathers the updated
+ * shards so that `params` is whole again.
+ *   grads, params : flat fp32 [n]; `params` MUST live in the arena (b2d_arena_alloc)
+ *   exp_avg, exp_avg_sq : fp32 [shard_off[rank+1]-shard_off[rank]], local */
+int b2d_sharded_step(b2d_ctx* ctx, int slot, const float* grads, float* params,
+                     float* exp_avg, float* exp_avg_sq, size_t n,
+                     const int64_t* shard_off, int wire, float scale,
+                     const b2d_adam* adam, void* wait_stream, void* comm_stream);
+
+/* K4 alone: out[0 .. len_r) = sum_r grads_r[shard_off[rank] ..) * scale  (fp32 out, local). */
+int b2d_reduce_scatter(b2d_ctx* ctx, int slot, const float* grads, float* out, size_t n,
+                       const int64_t* shard_off, int wire, float scale,
+                       void* wait_stream, void* comm_stream);
+
+/* K6 alone: `buf` (flat fp32 [n], in the arena) holds this rank's valid shard; pull every
+ * other shard from its owner. */
+int b2d_allgather(b2d_ctx* ctx, float* buf, size_t n, const int64_t* shard_off,
+                  void* wait_stream, void* comm_stream);
+
+/* All-ranks barrier enqueued on `stream` (also quiesces the arena before slots are re-laid out). */
+int b2d_barrier(b2d_ctx* ctx, void* stream);
+
+/* ---- symmetric arena ------------------------------------------------------------------- */
+
+/* Bump-allocate `bytes` (256-byte aligned) of caller-visible symmetric memory.  Every rank
+ * must make the same sequence of calls, so that offsets agree.  Never freed. */
+int b2d_arena_alloc(b2d_ctx* ctx, size_t bytes, void** dev_ptr, size_t* offset);
+/* Forget every bucket slot and arena allocation (host must have quiesced all ranks). */
+int b2d_arena_reset(b2d_ctx* ctx);
+
+/* ---- introspection --------------------------------------------------------------------- */
+
+typedef struct b2d_stats {
+  uint64_t launches;       /* kernels launched by this ctx since creation */
+  uint64_t timed_launches; /* launches bracketed by events (B2D_FLAG_TIMING) and resolved */
+  double timed_ms;         /* sum of their device durations */
+  uint64_t arena_bytes, arena_used;
+  int32_t world, rank, device, sm_count;
+  int32_t mem_kind;        /* 0 legacy IPC, 1 VMM */
+  int32_t mc_bound;        /* 1 when NVLS is usable */
+  int32_t last_algo, last_grid, last_block;
+} b2d_stats;
+
+int b2d_ctx_stats(b2d_ctx* ctx, b2d_stats* out);   /* resolves finished timing events */
+int b2d_ctx_reset_stats(b2d_ctx* ctx);
+/* The algorithm AUTO would pick and the grid it would launch, without launching. */
+int b2d_plan(b2d_ctx* ctx, size_t n, int wire, int algo, int* algo_out, int* grid_out, int* block_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2D_H_ */

@@ -1,0 +1,412 @@
+"""Tensor-level host side of the B200 gradient-sync path.
+
+* ``Communicator``   — one rank of a one-process-per-GPU job (the Ray-actor model of
+  ray_lightning/launchers/ray_launcher.py:105-114): creates the libb2d context, exchanges the
+  arena handles over the torch process group that ``RayStrategy._worker_setup`` already made
+  (ray_lightning/ray_ddp.py:192-196) and exposes allreduce / sharded-step calls on tensors.
+* ``LoopbackGroup``  — W ranks inside ONE process on ONE device (separate arenas, separate
+  streams).  Exercises the whole inter-rank protocol (barriers, slicing, double buffering)
+  on a single GPU; used by the parity tests and by ``bench.py`` at ``--gpus 1``.
+* ``B200HookState`` / ``b200_allreduce_hook`` — the torch DDP communication hook
+  (torch/nn/parallel/distributed.py:1987-2067) that replaces ``bf16_compress_hook`` /
+  the default allreduce with one fused kernel per bucket.
+
+No function here has a CPU implementation: tensors must be CUDA tensors and libb2d must load.
+"""
+import os
+import socket
+import struct
+import uuid
+
+import torch
+import torch.distributed as dist
+
+from . import _b2d
+from ._b2d import (ALGO_AUTO, ALGO_NAMES, ALGO_NVLS, ALGO_ONE_SHOT, ALGO_TWO_SHOT, FLAG_MEM_VMM,
+                   FLAG_TIMING, WIRE_BF16, WIRE_FP32, WIRE_NAMES, AdamParams, B2DError)
+
+__all__ = ["Communicator", "LoopbackGroup", "B200HookState", "b200_allreduce_hook", "arena_bytes_for",
+           "arena_tensor"]
+
+
+def _wire(w):
+    return WIRE_NAMES[w] if isinstance(w, str) else int(w)
+
+
+def _algo(a):
+    return ALGO_NAMES[a] if isinstance(a, str) else int(a)
+
+
+def arena_bytes_for(total_grad_elems, extra_bytes=0):
+    """Arena size for a model with that many gradient elements: a double-buffered staging copy
+    at up to 4 B/element, twice (DDP lays its buckets out anew once after the first iteration,
+    reducer.hpp:125-151), plus slack for alignment."""
+    return int(16 * total_grad_elems + (64 << 20) + extra_bytes)
+
+
+class _DevMem:
+    """Exposes a raw device range through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, ptr, nbytes, owner):
+        self._owner = owner  # keeps the libb2d context (and so the arena) alive
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                         "data": (int(ptr), False), "version": 2}
+
+
+def arena_tensor(ctx, numel, dtype, device):
+    """Allocate ``numel`` elements of ``dtype`` in the symmetric arena and view them as a tensor."""
+    nbytes = numel * torch.empty((), dtype=dtype).element_size()
+    ptr, off = ctx.arena_alloc(max(nbytes, 16))
+    t = torch.as_tensor(_DevMem(ptr, max(nbytes, 16), ctx), device=device)
+    return t[:nbytes].view(dtype), off
+
+
+def _check_tensor(t, device_index):
+    if not t.is_cuda:
+        raise ValueError("libb2d works on CUDA tensors only (got %s)" % t.device)
+    if t.device.index != device_index:
+        raise ValueError("tensor is on %s, communicator on cuda:%d" % (t.device, device_index))
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError("expected a contiguous float32 tensor")
+
+
+# ---- fd passing for VMM handles (SCM_RIGHTS over abstract unix sockets) -------------------
+def _sock_name(token, rank):
+    return "\0b2d-%s-%d" % (token, rank)
+
+
+def _exchange_fds(group, rank, world, token, my_fd, senders=None):
+    """Every rank in ``senders`` (default: all) gives ``my_fd`` to every other rank.
+    Returns {sender_rank: received_fd}."""
+    senders = list(range(world)) if senders is None else list(senders)
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(_sock_name(token, rank))
+    srv.listen(world + 1)
+    dist.barrier(group=group)  # everyone is listening
+    if rank in senders:
+        for p in range(world):
+            if p == rank:
+                continue
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            c.connect(_sock_name(token, p))
+            socket.send_fds(c, [struct.pack("i", rank)], [my_fd])
+            c.close()
+    got = {}
+    expect = len([s for s in senders if s != rank])
+    srv.settimeout(60.0)
+    for _ in range(expect):
+        conn, _addr = srv.accept()
+        msg, fds, _flags, _a = socket.recv_fds(conn, 4, 1)
+        conn.close()
+        got[struct.unpack("i", msg)[0]] = fds[0]
+    srv.close()
+    dist.barrier(group=group)
+    return got
+
+
+class _Base:
+    """Tensor-level calls shared by Communicator and the ranks of a LoopbackGroup."""
+
+    ctx = None
+    rank = 0
+    world = 1
+    device_index = 0
+
+    def allreduce_(self, buf, bucket_idx=0, wire="bf16", scale=None, algo="auto", wait_stream=None,
+                   comm_stream=None):
+        """In-place allreduce of one flat fp32 bucket: buf <- sum_r buf_r * scale (see b2d.h)."""
+        _check_tensor(buf, self.device_index)
+        scale = (1.0 / self.world) if scale is None else scale
+        ws = torch.cuda.current_stream(buf.device) if wait_stream is None else wait_stream
+        cs = ws if comm_stream is None else comm_stream
+        self.ctx.allreduce_bucket(bucket_idx, buf.data_ptr(), buf.numel(), _wire(wire), scale, _algo(algo), ws, cs)
+        return buf
+
+    def sharded_step_(self, grads, params, exp_avg, exp_avg_sq, shard_off, step, lr, betas=(0.9, 0.999),
+                      eps=1e-8, weight_decay=0.0, adamw=False, zero_grads=False, wire="bf16", scale=None,
+                      slot=0, wait_stream=None, comm_stream=None):
+        """reduce-scatter -> partitioned Adam -> parameter all-gather, one kernel (b2d_sharded_step)."""
+        for t in (grads, params, exp_avg, exp_avg_sq):
+            _check_tensor(t, self.device_index)
+        scale = (1.0 / self.world) if scale is None else scale
+        ws = torch.cuda.current_stream(grads.device) if wait_stream is None else wait_stream
+        cs = ws if comm_stream is None else comm_stream
+        adam = AdamParams(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay,
+                          step=int(step), adamw=int(bool(adamw)), zero_grads=int(bool(zero_grads)))
+        self.ctx.sharded_step(slot, grads.data_ptr(), params.data_ptr(), exp_avg.data_ptr(),
+                              exp_avg_sq.data_ptr(), grads.numel(), shard_off, _wire(wire), scale, adam, ws, cs)
+
+    def reduce_scatter(self, grads, out, shard_off, wire="fp32", scale=None, slot=0, wait_stream=None,
+                       comm_stream=None):
+        _check_tensor(grads, self.device_index)
+        _check_tensor(out, self.device_index)
+        scale = (1.0 / self.world) if scale is None else scale
+        ws = torch.cuda.current_stream(grads.device) if wait_stream is None else wait_stream
+        cs = ws if comm_stream is None else comm_stream
+        self.ctx.reduce_scatter(slot, grads.data_ptr(), out.data_ptr(), grads.numel(), shard_off,
+                                _wire(wire), scale, ws, cs)
+        return out
+
+    def allgather_(self, buf, shard_off, wait_stream=None, comm_stream=None):
+        _check_tensor(buf, self.device_index)
+        ws = torch.cuda.current_stream(buf.device) if wait_stream is None else wait_stream
+        cs = ws if comm_stream is None else comm_stream
+        self.ctx.allgather(buf.data_ptr(), buf.numel(), shard_off, ws, cs)
+        return buf
+
+    def arena_tensor(self, numel, dtype=torch.float32):
+        t, _ = arena_tensor(self.ctx, numel, dtype, torch.device("cuda", self.device_index))
+        return t
+
+    def device_barrier(self, stream=None):
+        st = torch.cuda.current_stream(torch.device("cuda", self.device_index)) if stream is None else stream
+        self.ctx.barrier(st)
+
+    def stats(self):
+        return self.ctx.stats()
+
+
+class Communicator(_Base):
+    """One rank of a one-process-per-GPU job.
+
+    ``group`` is an initialised torch.distributed group (gloo or nccl) used ONLY as control
+    plane: handle exchange and host barriers.  No gradient byte ever goes through it.
+    """
+
+    def __init__(self, rank, world, device_index, arena_bytes, group=None, mem="ipc", timing=False,
+                 nvls="auto", timeout_ms=None, max_ctas=None, one_shot_max_bytes=None):
+        if not torch.cuda.is_available():
+            raise _b2d.B2DUnavailableError("CUDA is not available: the B200 gradient-sync path has no CPU fallback")
+        self.rank, self.world, self.device_index = rank, world, device_index
+        self.group = group
+        self.mem = mem
+        flags = (FLAG_MEM_VMM if mem == "vmm" else 0) | (FLAG_TIMING if timing else 0)
+        self.ctx = _b2d.Context(rank, world, device_index, arena_bytes, flags)
+        self.nvls = False
+        if timeout_ms is not None:
+            self.ctx.set_timeout_ms(timeout_ms)
+        if max_ctas is not None:
+            self.ctx.set_max_ctas(max_ctas)
+        if one_shot_max_bytes is not None:
+            self.ctx.set_one_shot_max_bytes(one_shot_max_bytes)
+        if world > 1:
+            self._connect(nvls)
+
+    def _connect(self, nvls):
+        if not dist.is_initialized():
+            raise RuntimeError("Communicator needs an initialised torch.distributed process group "
+                               "(RayStrategy._worker_setup creates it)")
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, self.ctx.export_handle(), group=self.group)
+        fds = {}
+        token = None
+        if self.mem == "vmm":
+            tok = [uuid.uuid4().hex[:12] if self.rank == 0 else None]
+            dist.broadcast_object_list(tok, src=0, group=self.group)
+            token = tok[0]
+            fds = _exchange_fds(self.group, self.rank, self.world, token + "a", self.ctx.export_fd())
+        for p in range(self.world):
+            if p != self.rank:
+                self.ctx.import_handle(p, blobs[p], fds.get(p))
+        for fd in fds.values():
+            os.close(fd)
+        self.ctx.finalize()
+        dist.barrier(group=self.group)
+        if self.mem == "vmm" and nvls in ("auto", True, "on"):
+            self._try_nvls(token, required=nvls in (True, "on"))
+
+    def _try_nvls(self, token, required):
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(self.ctx.mc_supported()), group=self.group)
+        ok = all(flags)
+        err = None
+        fd = -1
+        if ok and self.rank == 0:
+            try:
+                fd = self.ctx.mc_create()
+            except B2DError as e:
+                err = str(e)
+        st = [err is None and ok]
+        dist.broadcast_object_list(st, src=0, group=self.group)
+        if not st[0]:
+            if required:
+                raise RuntimeError("NVLS multicast is not available on this box: %s" % (err or "unsupported"))
+            return
+        got = _exchange_fds(self.group, self.rank, self.world, token + "m", fd if self.rank == 0 else -1, senders=[0])
+        try:
+            self.ctx.mc_join(fd if self.rank == 0 else got[0])
+            joined = True
+        except B2DError as e:
+            joined, err = False, str(e)
+        allj = [None] * self.world
+        dist.all_gather_object(allj, joined, group=self.group)  # also: every device has been added
+        if all(allj):
+            try:
+                self.ctx.mc_bind()
+                bound = True
+            except B2DError as e:
+                bound, err = False, str(e)
+            allb = [None] * self.world
+            dist.all_gather_object(allb, bound, group=self.group)
+            self.nvls = all(allb)
+        for f in ([fd] if self.rank == 0 else list(got.values())):
+            if f is not None and f >= 0:
+                os.close(f)
+        if required and not self.nvls:
+            raise RuntimeError("NVLS multicast setup failed: %s" % err)
+
+    def close(self):
+        if self.ctx is not None:
+            if self.world > 1 and dist.is_initialized():
+                try:
+                    torch.cuda.synchronize(self.device_index)
+                    dist.barrier(group=self.group)
+                except Exception:
+                    pass
+            self.ctx.destroy()
+            self.ctx = None
+
+
+class _LoopRank(_Base):
+    def __init__(self, ctx, rank, world, device_index, stream):
+        self.ctx, self.rank, self.world, self.device_index, self.stream = ctx, rank, world, device_index, stream
+
+
+class LoopbackGroup:
+    """``world`` ranks in this process, all on ``device_index``; rank r launches on its own stream.
+
+    Co-residency: W ranks x grid CTAs x 512 threads must fit the device at once (the kernels
+    spin on each other), so the per-kernel CTA budget is 128 // W."""
+
+    def __init__(self, world, device_index=0, arena_bytes=64 << 20, timing=False, timeout_ms=5000,
+                 max_ctas=None, devices=None):
+        if not torch.cuda.is_available():
+            raise _b2d.B2DUnavailableError("CUDA is not available")
+        self.world = world
+        devices = [device_index] * world if devices is None else list(devices)
+        flags = FLAG_TIMING if timing else 0
+        self.ranks = []
+        for r in range(world):
+            with torch.cuda.device(devices[r]):
+                ctx = _b2d.Context(r, world, devices[r], arena_bytes, flags)
+                ctx.set_timeout_ms(timeout_ms)
+                same_dev = len(set(devices)) == 1
+                ctx.set_max_ctas(max_ctas if max_ctas is not None else (max(1, 128 // world) if same_dev else 64))
+                self.ranks.append(_LoopRank(ctx, r, world, devices[r], torch.cuda.Stream(device=devices[r])))
+        blobs = [rk.ctx.export_handle() for rk in self.ranks]
+        for rk in self.ranks:
+            for p in range(world):
+                if p != rk.rank:
+                    rk.ctx.import_handle(p, blobs[p])
+            rk.ctx.finalize()
+
+    def allreduce_(self, bufs, bucket_idx=0, wire="bf16", scale=None, algo="auto"):
+        """bufs[r] is rank r's bucket; all are reduced in place. Asynchronous."""
+        for rk, b in zip(self.ranks, bufs):
+            rk.allreduce_(b, bucket_idx, wire, scale, algo,
+                          wait_stream=torch.cuda.current_stream(b.device), comm_stream=rk.stream)
+        return bufs
+
+    def sharded_step_(self, grads, params, exp_avg, exp_avg_sq, shard_off, **kw):
+        for r, rk in enumerate(self.ranks):
+            rk.sharded_step_(grads[r], params[r], exp_avg[r], exp_avg_sq[r], shard_off,
+                             wait_stream=torch.cuda.current_stream(grads[r].device), comm_stream=rk.stream, **kw)
+
+    def reduce_scatter(self, grads, outs, shard_off, **kw):
+        for r, rk in enumerate(self.ranks):
+            rk.reduce_scatter(grads[r], outs[r], shard_off,
+                              wait_stream=torch.cuda.current_stream(grads[r].device), comm_stream=rk.stream, **kw)
+
+    def allgather_(self, bufs, shard_off):
+        for r, rk in enumerate(self.ranks):
+            rk.allgather_(bufs[r], shard_off, wait_stream=torch.cuda.current_stream(bufs[r].device),
+                          comm_stream=rk.stream)
+
+    def synchronize(self):
+        for rk in self.ranks:
+            rk.stream.synchronize()
+
+    def join_current_stream(self):
+        """Make the caller's current stream(s) wait for every rank's comm stream."""
+        for rk in self.ranks:
+            torch.cuda.current_stream(torch.device("cuda", rk.device_index)).wait_stream(rk.stream)
+
+    def close(self):
+        self.synchronize()
+        for rk in self.ranks:
+            rk.ctx.destroy()
+        self.ranks = []
+
+
+# ---- the DDP communication hook -----------------------------------------------------------
+class B200HookState:
+    """State object handed to ``DistributedDataParallel.register_comm_hook``.
+
+    wire  "bf16": same arithmetic contract as torch's ``bf16_compress_hook`` (bf16 on the wire,
+                  fp32 accumulate, one rounding of the sum); "fp32": contract of DDP's default
+                  allreduce (divide, then fp32 SUM).
+    The communicator is created lazily on first use *inside the worker*: the strategy object is
+    pickled to every actor (ray_launcher.py:240-245) and must not hold CUDA handles before that.
+    """
+
+    def __init__(self, wire="bf16", algo="auto", process_group=None, total_grad_elems=None,
+                 arena_bytes=None, mem="ipc", timing=False, max_ctas=None, one_shot_max_bytes=None,
+                 nvls="auto", stream_priority=-1):
+        self.wire, self.algo = wire, algo
+        self.process_group = process_group
+        self.total_grad_elems = total_grad_elems
+        self.arena_bytes = arena_bytes
+        self.mem, self.timing, self.max_ctas, self.nvls = mem, timing, max_ctas, nvls
+        self.one_shot_max_bytes = one_shot_max_bytes
+        self.stream_priority = stream_priority
+        self.comm = None
+        self.stream = None
+        self.calls = 0
+
+    def ensure(self, device):
+        if self.comm is not None:
+            return
+        world = dist.get_world_size(self.process_group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.process_group) if dist.is_initialized() else 0
+        nbytes = self.arena_bytes
+        if nbytes is None:
+            if self.total_grad_elems is None:
+                raise ValueError("B200HookState needs total_grad_elems or arena_bytes")
+            nbytes = arena_bytes_for(self.total_grad_elems)
+        self.comm = Communicator(rank, world, device.index, nbytes, group=self.process_group, mem=self.mem,
+                                 timing=self.timing, nvls=self.nvls, max_ctas=self.max_ctas,
+                                 one_shot_max_bytes=self.one_shot_max_bytes)
+        # a high-priority side stream: the comm kernel's few CTAs get SMs as soon as backward frees any
+        self.stream = torch.cuda.Stream(device=device, priority=self.stream_priority)
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["comm"], d["stream"] = None, None
+        return d
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
+
+
+def b200_allreduce_hook(state: B200HookState, bucket: dist.GradBucket) -> torch.futures.Future[torch.Tensor]:
+    """DDP comm hook: one fused libb2d kernel per bucket on a side stream.
+
+    Replaces (ray_lightning/ray_ddp.py:112-116 -> torch DDP) ``bf16_compress_hook``'s
+    cast + div + ncclAllReduce + copy (default_hooks.py:57-93,116-134) or, with wire="fp32",
+    the default divide + fp32 allreduce (default_hooks.py:18-54).  Called once per bucket in
+    bucket order on the autograd thread (reducer.hpp:112-113); returns a CUDA future that the
+    Reducer's finalize_backward turns into a stream wait.
+    """
+    buf = bucket.buffer()
+    state.ensure(buf.device)
+    comm = state.comm
+    cur = torch.cuda.current_stream(buf.device)
+    comm.allreduce_(buf, bucket.index(), wire=state.wire, scale=1.0 / comm.world, algo=state.algo,
+                    wait_stream=cur, comm_stream=state.stream)
+    state.calls += 1
+    fut = torch.futures.Future(devices=[buf.device])
+    with torch.cuda.stream(state.stream):
+        fut.set_result(buf)
+    return fut

@@ -1,0 +1,995 @@
+// b2d.cu — host side of libb2d: context, symmetric arena, peer mapping (CUDA IPC / VMM fd /
+// same-process), NVLS multicast binding, slot bookkeeping and the kernel launches.
+// C ABI declared in include/b2d.h.  No torch, no pybind: plain CUDA runtime (static) plus the
+// driver's VMM/multicast entry points resolved at run time (libcuda is not linked, so the
+// library loads — and its symbols can be checked — on a box without a GPU driver).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b2d_kernels.cuh"
+
+using namespace b2d;
+
+namespace {
+
+constexpr uint32_t kMagic = 0x42324431u;  // "B2D1"
+constexpr size_t kAlign = 256;
+constexpr size_t kArenaGranule = 2u << 20;
+
+thread_local std::string g_create_error;
+
+struct HandleBlob {
+  uint32_t magic;
+  uint32_t version;
+  int32_t rank, world, device, mem_kind;
+  int64_t pid;
+  uint64_t arena_bytes;
+  uint64_t arena_ptr;    // valid inside the exporting process only
+  uint64_t vmm_handle;   // CUmemGenericAllocationHandle, exporting process only
+  int32_t fd;            // POSIX fd of the VMM allocation *in the importing process* (patched)
+  int32_t pad;
+  cudaIpcMemHandle_t ipc;
+  unsigned char reserved[B2D_HANDLE_BYTES - 64 - sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(HandleBlob) == B2D_HANDLE_BYTES, "handle blob size is part of the ABI");
+
+// ---- driver entry points (VMM + multicast), resolved lazily ------------------------------
+struct Driver {
+  bool tried = false, ok = false;
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle);
+  CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t);
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+  CUresult (*MemUnmap)(CUdeviceptr, size_t);
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+  CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+  CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long);
+  CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType);
+  CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*);
+  CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice);
+  CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long);
+  CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t);
+  CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags);
+  CUresult (*DeviceGet)(CUdevice*, int);
+  CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice);
+  CUresult (*GetErrorString)(CUresult, const char**);
+};
+Driver g_drv;
+std::mutex g_drv_mu;
+
+template <typename F>
+bool resolve(const char* name, F* fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr ||
+      q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  *fn = reinterpret_cast<F>(p);
+  return true;
+}
+
+bool driver_ready() {
+  std::lock_guard<std::mutex> lk(g_drv_mu);
+  if (g_drv.tried) return g_drv.ok;
+  g_drv.tried = true;
+  bool ok = true;
+  ok &= resolve("cuMemCreate", &g_drv.MemCreate);
+  ok &= resolve("cuMemRelease", &g_drv.MemRelease);
+  ok &= resolve("cuMemAddressReserve", &g_drv.MemAddressReserve);
+  ok &= resolve("cuMemAddressFree", &g_drv.MemAddressFree);
+  ok &= resolve("cuMemMap", &g_drv.MemMap);
+  ok &= resolve("cuMemUnmap", &g_drv.MemUnmap);
+  ok &= resolve("cuMemSetAccess", &g_drv.MemSetAccess);
+  ok &= resolve("cuMemGetAllocationGranularity", &g_drv.MemGetAllocationGranularity);
+  ok &= resolve("cuMemExportToShareableHandle", &g_drv.MemExportToShareableHandle);
+  ok &= resolve("cuMemImportFromShareableHandle", &g_drv.MemImportFromShareableHandle);
+  ok &= resolve("cuDeviceGet", &g_drv.DeviceGet);
+  ok &= resolve("cuDeviceGetAttribute", &g_drv.DeviceGetAttribute);
+  ok &= resolve("cuGetErrorString", &g_drv.GetErrorString);
+  // multicast is optional
+  if (!(resolve("cuMulticastCreate", &g_drv.MulticastCreate) &&
+        resolve("cuMulticastAddDevice", &g_drv.MulticastAddDevice) &&
+        resolve("cuMulticastBindMem", &g_drv.MulticastBindMem) &&
+        resolve("cuMulticastUnbind", &g_drv.MulticastUnbind) &&
+        resolve("cuMulticastGetGranularity", &g_drv.MulticastGetGranularity))) {
+    g_drv.MulticastCreate = nullptr;
+  }
+  g_drv.ok = ok;
+  return ok;
+}
+
+const char* cu_err(CUresult r) {
+  const char* s = nullptr;
+  if (g_drv.GetErrorString != nullptr && g_drv.GetErrorString(r, &s) == CUDA_SUCCESS && s) return s;
+  return "unknown CUresult";
+}
+
+struct Slot {
+  size_t off = 0;      // byte offset of the double buffer inside the arena
+  size_t half = 0;     // bytes of one half
+  size_t n = 0;
+  int wire = -1, algo = -1, grid = 0;
+  unsigned parity = 0;
+};
+
+enum PeerMap { kMapNone = 0, kMapSelf, kMapDirect, kMapLegacyIpc, kMapVmm };
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+struct b2d_ctx {
+  int rank = 0, world = 1, device = 0;
+  unsigned flags = 0;
+  int sm_count = 0;
+  int mem_kind = 0;
+  size_t arena_bytes = 0;
+  unsigned char* arena = nullptr;
+  CUmemGenericAllocationHandle vmm_handle = 0;
+  int own_fd = -1;
+  Peers peers{};
+  PeerMap peer_map[B2D_MAX_WORLD] = {};
+  CUmemGenericAllocationHandle peer_vmm[B2D_MAX_WORLD] = {};
+  bool finalized = false;
+
+  // multicast
+  CUmemGenericAllocationHandle mc_handle = 0;
+  bool mc_joined = false, mc_bound = false;
+  size_t mc_size = 0;
+
+  Diag* diag_host = nullptr;
+  Diag* diag_dev = nullptr;
+
+  cudaEvent_t wait_ev[8] = {};
+  unsigned wait_ev_idx = 0;
+
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_free, ev_pending;
+  uint64_t launches = 0, timed_launches = 0;
+  double timed_ms = 0.0;
+
+  std::map<int, Slot> slots;
+  size_t slot_top = 0;     // slots grow up from just above the signal pad
+  size_t user_bottom = 0;  // user allocations grow down from the end of the arena
+
+  int max_ctas = 64;
+  size_t one_shot_max_bytes = 256 * 1024;
+  unsigned timeout_ms = 10000;
+  int last_algo = 0, last_grid = 0, last_block = 0;
+
+  std::string err;
+  std::mutex mu;
+};
+
+namespace {
+
+int fail(b2d_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx != nullptr) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define B2D_CUDA(ctx, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      cudaGetLastError();                                                                    \
+      return fail((ctx), B2D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                       \
+    }                                                                                        \
+  } while (0)
+
+#define B2D_CU(ctx, expr)                                                                    \
+  do {                                                                                       \
+    CUresult r__ = (expr);                                                                   \
+    if (r__ != CUDA_SUCCESS)                                                                 \
+      return fail((ctx), B2D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cu_err(r__), __FILE__, \
+                  __LINE__);                                                                 \
+  } while (0)
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int vmm_map(b2d_ctx* ctx, CUmemGenericAllocationHandle h, size_t bytes, int device, unsigned char** out) {
+  CUdeviceptr va = 0;
+  B2D_CU(ctx, g_drv.MemAddressReserve(&va, bytes, kArenaGranule, 0, 0));
+  CUresult r = g_drv.MemMap(va, bytes, 0, h, 0);
+  if (r != CUDA_SUCCESS) {
+    g_drv.MemAddressFree(va, bytes);
+    return fail(ctx, B2D_ERR_CUDA, "cuMemMap failed: %s", cu_err(r));
+  }
+  CUmemAccessDesc desc{};
+  desc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  desc.location.id = device;
+  desc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  r = g_drv.MemSetAccess(va, bytes, &desc, 1);
+  if (r != CUDA_SUCCESS) {
+    g_drv.MemUnmap(va, bytes);
+    g_drv.MemAddressFree(va, bytes);
+    return fail(ctx, B2D_ERR_CUDA, "cuMemSetAccess failed: %s", cu_err(r));
+  }
+  *out = reinterpret_cast<unsigned char*>(va);
+  return B2D_OK;
+}
+
+void vmm_unmap(unsigned char* p, size_t bytes) {
+  if (p == nullptr) return;
+  g_drv.MemUnmap(reinterpret_cast<CUdeviceptr>(p), bytes);
+  g_drv.MemAddressFree(reinterpret_cast<CUdeviceptr>(p), bytes);
+}
+
+void resolve_timing(b2d_ctx* ctx, bool block) {
+  size_t keep = 0;
+  for (size_t i = 0; i < ctx->ev_pending.size(); ++i) {
+    auto& pr = ctx->ev_pending[i];
+    cudaError_t q = block ? cudaEventSynchronize(pr.second) : cudaEventQuery(pr.second);
+    if (q == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+        ctx->timed_ms += ms;
+        ctx->timed_launches += 1;
+      } else {
+        cudaGetLastError();
+      }
+      ctx->ev_free.push_back(pr);
+    } else {
+      if (q != cudaErrorNotReady) cudaGetLastError(); else cudaGetLastError();
+      ctx->ev_pending[keep++] = pr;
+    }
+  }
+  ctx->ev_pending.resize(keep);
+}
+
+// Everything a launch needs around the kernel itself: stream dependency + optional timing.
+struct LaunchScope {
+  b2d_ctx* ctx;
+  cudaStream_t comm;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  bool timing = false;
+  int begin(void* wait_stream, void* comm_stream) {
+    comm = static_cast<cudaStream_t>(comm_stream);
+    cudaStream_t ws = static_cast<cudaStream_t>(wait_stream);
+    if (ws != comm) {
+      cudaEvent_t e = ctx->wait_ev[ctx->wait_ev_idx++ % 8];
+      B2D_CUDA(ctx, cudaEventRecord(e, ws));
+      B2D_CUDA(ctx, cudaStreamWaitEvent(comm, e, 0));
+    }
+    if (ctx->flags & B2D_FLAG_TIMING) {
+      if (ctx->ev_free.empty() && ctx->ev_pending.size() >= 4096) resolve_timing(ctx, false);
+      if (ctx->ev_free.empty() && ctx->ev_pending.size() < 4096) {
+        cudaEvent_t a, b;
+        B2D_CUDA(ctx, cudaEventCreate(&a));
+        B2D_CUDA(ctx, cudaEventCreate(&b));
+        ctx->ev_free.emplace_back(a, b);
+      }
+      if (!ctx->ev_free.empty()) {
+        ev = ctx->ev_free.back();
+        ctx->ev_free.pop_back();
+        timing = true;
+        B2D_CUDA(ctx, cudaEventRecord(ev.first, comm));
+      }
+    }
+    return B2D_OK;
+  }
+  int end() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches += 1;
+    if (timing) {
+      B2D_CUDA(ctx, cudaEventRecord(ev.second, comm));
+      ctx->ev_pending.push_back(ev);
+    }
+    return B2D_OK;
+  }
+};
+
+ArParams make_ar_params(b2d_ctx* ctx) {
+  ArParams P{};
+  P.rank = ctx->rank;
+  P.world = ctx->world;
+  P.timeout_ns = static_cast<unsigned long long>(ctx->timeout_ms) * 1000000ull;
+  P.diag = ctx->diag_dev;
+  P.peers = ctx->peers;
+  return P;
+}
+
+int launch_barrier(b2d_ctx* ctx, cudaStream_t stream) {
+  ArParams P = make_ar_params(ctx);
+  barrier_kernel<<<B2D_MAX_BLOCKS, 32, 0, stream>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, "barrier launch failed: %s", cudaGetErrorString(e));
+  ctx->launches += 1;
+  return B2D_OK;
+}
+
+int pick_algo(b2d_ctx* ctx, size_t n, int wire, int algo) {
+  if (ctx->world == 1) return B2D_ALGO_ONE_SHOT;
+  if (algo != B2D_ALGO_AUTO) return algo;
+  const size_t wire_bytes = n * (wire == B2D_WIRE_BF16 ? 2 : 4);
+  if (wire_bytes <= ctx->one_shot_max_bytes) return B2D_ALGO_ONE_SHOT;
+  if (ctx->mc_bound) return B2D_ALGO_NVLS;
+  return B2D_ALGO_TWO_SHOT;
+}
+
+int pick_grid(b2d_ctx* ctx, size_t n, int wire, int algo) {
+  const size_t epp = wire == B2D_WIRE_BF16 ? 8 : 4;
+  const size_t npacks = (n + epp - 1) / epp;
+  size_t work = npacks;
+  if (algo != B2D_ALGO_ONE_SHOT) work = (npacks + ctx->world - 1) / ctx->world;
+  size_t grid = (work + kThreads - 1) / kThreads;
+  if (grid < 1) grid = 1;
+  if (grid > static_cast<size_t>(ctx->max_ctas)) grid = ctx->max_ctas;
+  return static_cast<int>(grid);
+}
+
+// Arena slot of a bucket: two halves used alternately, so that a rank may start staging
+// step k+1 while a slow peer still reads step k's payload.
+int get_slot(b2d_ctx* ctx, int key, size_t half_bytes, size_t n, int wire, int algo, int grid,
+             cudaStream_t stream, size_t* stage_off) {
+  half_bytes = round_up(half_bytes, kAlign);
+  Slot& s = ctx->slots[key];
+  const bool same = s.half >= half_bytes && s.n == n && s.wire == wire && s.algo == algo && s.grid == grid;
+  if (!same) {
+    if (s.half != 0) {
+      // geometry changed (DDP rebuilt its buckets, reducer.hpp:125-151): peers may still read
+      // the old layout of this region — meet them before anything is re-mapped
+      int rc = launch_barrier(ctx, stream);
+      if (rc != B2D_OK) return rc;
+    }
+    if (s.half < half_bytes) {
+      if (ctx->slot_top + 2 * half_bytes > ctx->user_bottom)
+        return fail(ctx, B2D_ERR_NOMEM,
+                    "symmetric arena exhausted: slot %d needs 2 x %zu bytes, %zu free of %zu", key,
+                    half_bytes, ctx->user_bottom - ctx->slot_top, ctx->arena_bytes);
+      s.off = ctx->slot_top;
+      s.half = half_bytes;
+      ctx->slot_top += 2 * half_bytes;
+    }
+    s.n = n; s.wire = wire; s.algo = algo; s.grid = grid;
+  }
+  *stage_off = s.off + (s.parity & 1u) * s.half;
+  s.parity ^= 1u;
+  return B2D_OK;
+}
+
+template <bool BF16, bool NVLS>
+void launch_two_shot(const ArParams& P, int world, int grid, cudaStream_t st) {
+  switch (world) {
+    case 2: k2_two_shot_kernel<2, BF16, NVLS><<<grid, kThreads, 0, st>>>(P); break;
+    case 4: k2_two_shot_kernel<4, BF16, NVLS><<<grid, kThreads, 0, st>>>(P); break;
+    case 8: k2_two_shot_kernel<8, BF16, NVLS><<<grid, kThreads, 0, st>>>(P); break;
+    default: k2_two_shot_kernel<0, BF16, NVLS><<<grid, kThreads, 0, st>>>(P); break;
+  }
+}
+template <bool BF16>
+void launch_one_shot(const ArParams& P, int world, int grid, cudaStream_t st) {
+  switch (world) {
+    case 2: k1_one_shot_kernel<2, BF16><<<grid, kThreads, 0, st>>>(P); break;
+    case 4: k1_one_shot_kernel<4, BF16><<<grid, kThreads, 0, st>>>(P); break;
+    case 8: k1_one_shot_kernel<8, BF16><<<grid, kThreads, 0, st>>>(P); break;
+    default: k1_one_shot_kernel<0, BF16><<<grid, kThreads, 0, st>>>(P); break;
+  }
+}
+template <bool BF16>
+void launch_sharded(const ShParams& P, int world, int grid, cudaStream_t st) {
+  switch (world) {
+    case 2: k456_sharded_kernel<2, BF16><<<grid, kThreads, 0, st>>>(P); break;
+    case 4: k456_sharded_kernel<4, BF16><<<grid, kThreads, 0, st>>>(P); break;
+    case 8: k456_sharded_kernel<8, BF16><<<grid, kThreads, 0, st>>>(P); break;
+    default: k456_sharded_kernel<0, BF16><<<grid, kThreads, 0, st>>>(P); break;
+  }
+}
+
+int check_ready(b2d_ctx* ctx) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  if (!ctx->finalized) return fail(ctx, B2D_ERR_STATE, "b2d_ctx_finalize() has not been called");
+  if (ctx->diag_host != nullptr && ctx->diag_host->code != 0)
+    return fail(ctx, B2D_ERR_PEER,
+                "peer timeout recorded: rank %u block %u waited for peer %u (expected epoch %u, saw %u)",
+                ctx->diag_host->rank, ctx->diag_host->block, ctx->diag_host->peer,
+                ctx->diag_host->expect, ctx->diag_host->got);
+  return B2D_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int b2d_version(void) { return B2D_VERSION; }
+
+const char* b2d_last_error(b2d_ctx* ctx) {
+  return ctx != nullptr ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int b2d_ctx_create(int rank, int world, int device, size_t arena_bytes, unsigned flags, b2d_ctx** out) {
+  if (out == nullptr) return fail(nullptr, B2D_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (world < 1 || world > B2D_MAX_WORLD || rank < 0 || rank >= world)
+    return fail(nullptr, B2D_ERR_INVALID, "bad rank/world %d/%d (max world %d)", rank, world, B2D_MAX_WORLD);
+  int ndev = 0;
+  {
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(nullptr, B2D_ERR_CUDA, "no usable CUDA device: %s", cudaGetErrorString(e));
+    }
+  }
+  if (device < 0 || device >= ndev) return fail(nullptr, B2D_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  B2D_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, B2D_ERR_UNSUPPORTED, "libb2d is built for sm_100a; device %d is sm_%d%d", device, prop.major, prop.minor);
+
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(nullptr, B2D_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  B2D_CUDA(nullptr, cudaFree(0));  // make sure the primary context exists
+
+  b2d_ctx* ctx = new b2d_ctx();
+  ctx->rank = rank; ctx->world = world; ctx->device = device; ctx->flags = flags;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->mem_kind = (flags & B2D_FLAG_MEM_VMM) ? 1 : 0;
+  ctx->arena_bytes = round_up(arena_bytes + kSignalBytes, kArenaGranule);
+
+  auto bail = [&](int code) { std::string m = ctx->err; b2d_ctx_destroy(ctx); g_create_error = m; return code; };
+
+  if (ctx->mem_kind == 1) {
+    if (!driver_ready()) return bail(fail(ctx, B2D_ERR_UNSUPPORTED, "CUDA VMM driver entry points not available"));
+    CUmemAllocationProp ap{};
+    ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ap.location.id = device;
+    ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = kArenaGranule;
+    if (g_drv.MemGetAllocationGranularity(&gran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && gran > 0)
+      ctx->arena_bytes = round_up(ctx->arena_bytes, gran);
+    if (g_drv.MulticastCreate != nullptr) {
+      CUmulticastObjectProp mp{};
+      mp.numDevices = world > 1 ? world : 2;
+      mp.size = ctx->arena_bytes;
+      mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+      size_t mg = 0;
+      if (g_drv.MulticastGetGranularity(&mg, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && mg > 0)
+        ctx->arena_bytes = round_up(ctx->arena_bytes, mg);
+    }
+    CUresult r = g_drv.MemCreate(&ctx->vmm_handle, ctx->arena_bytes, &ap, 0);
+    if (r != CUDA_SUCCESS) return bail(fail(ctx, B2D_ERR_CUDA, "cuMemCreate(%zu) failed: %s", ctx->arena_bytes, cu_err(r)));
+    int rc = vmm_map(ctx, ctx->vmm_handle, ctx->arena_bytes, device, &ctx->arena);
+    if (rc != B2D_OK) return bail(rc);
+  } else {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, ctx->arena_bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, B2D_ERR_CUDA, "cudaMalloc(%zu) failed: %s", ctx->arena_bytes, cudaGetErrorString(e))); }
+    ctx->arena = static_cast<unsigned char*>(p);
+  }
+  {
+    // only the signal pad has to start at zero
+    cudaError_t e = cudaMemset(ctx->arena, 0, kSignalBytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, B2D_ERR_CUDA, "arena memset failed: %s", cudaGetErrorString(e))); }
+  }
+  ctx->peers.arena[rank] = ctx->arena;
+  ctx->peers.signal[rank] = reinterpret_cast<Signal*>(ctx->arena);
+  ctx->peer_map[rank] = kMapSelf;
+  ctx->slot_top = kSignalBytes;
+  ctx->user_bottom = ctx->arena_bytes;
+
+  {
+    void* h = nullptr;
+    cudaError_t e = cudaHostAlloc(&h, sizeof(Diag), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+      memset(h, 0, sizeof(Diag));
+      ctx->diag_host = static_cast<Diag*>(h);
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) ctx->diag_dev = static_cast<Diag*>(d);
+      else cudaGetLastError();
+    } else {
+      cudaGetLastError();
+    }
+  }
+  for (auto& e : ctx->wait_ev) {
+    cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (r != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, B2D_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(r))); }
+  }
+  if (world == 1) ctx->finalized = true;
+  *out = ctx;
+  return B2D_OK;
+}
+
+int b2d_ctx_export(b2d_ctx* ctx, void* handle_buf, size_t* len) {
+  if (ctx == nullptr || handle_buf == nullptr || len == nullptr) return fail(ctx, B2D_ERR_INVALID, "NULL argument");
+  if (*len < sizeof(HandleBlob)) return fail(ctx, B2D_ERR_INVALID, "handle buffer too small: %zu < %zu", *len, sizeof(HandleBlob));
+  DeviceGuard guard(ctx->device);
+  HandleBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = kMagic; b.version = B2D_VERSION;
+  b.rank = ctx->rank; b.world = ctx->world; b.device = ctx->device; b.mem_kind = ctx->mem_kind;
+  b.pid = static_cast<int64_t>(getpid());
+  b.arena_bytes = ctx->arena_bytes;
+  b.arena_ptr = reinterpret_cast<uint64_t>(ctx->arena);
+  b.vmm_handle = static_cast<uint64_t>(ctx->vmm_handle);
+  b.fd = -1;
+  if (ctx->mem_kind == 0) B2D_CUDA(ctx, cudaIpcGetMemHandle(&b.ipc, ctx->arena));
+  memcpy(handle_buf, &b, sizeof(b));
+  *len = sizeof(b);
+  return B2D_OK;
+}
+
+int b2d_ctx_export_fd(b2d_ctx* ctx, int* fd_out) {
+  if (ctx == nullptr || fd_out == nullptr) return fail(ctx, B2D_ERR_INVALID, "NULL argument");
+  if (ctx->mem_kind != 1) return fail(ctx, B2D_ERR_STATE, "context was not created with B2D_FLAG_MEM_VMM");
+  if (ctx->own_fd < 0) {
+    int fd = -1;
+    B2D_CU(ctx, g_drv.MemExportToShareableHandle(&fd, ctx->vmm_handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+    ctx->own_fd = fd;
+  }
+  *fd_out = ctx->own_fd;
+  return B2D_OK;
+}
+
+int b2d_handle_set_fd(void* handle_buf, size_t len, int fd) {
+  if (handle_buf == nullptr || len < sizeof(HandleBlob)) return fail(nullptr, B2D_ERR_INVALID, "bad handle buffer");
+  HandleBlob* b = static_cast<HandleBlob*>(handle_buf);
+  if (b->magic != kMagic) return fail(nullptr, B2D_ERR_INVALID, "not a b2d handle");
+  b->fd = fd;
+  return B2D_OK;
+}
+
+int b2d_ctx_import(b2d_ctx* ctx, int peer, const void* handle_buf, size_t len) {
+  if (ctx == nullptr || handle_buf == nullptr) return fail(ctx, B2D_ERR_INVALID, "NULL argument");
+  if (len < sizeof(HandleBlob)) return fail(ctx, B2D_ERR_INVALID, "handle too short");
+  if (peer < 0 || peer >= ctx->world || peer == ctx->rank) return fail(ctx, B2D_ERR_INVALID, "bad peer %d", peer);
+  if (ctx->peer_map[peer] != kMapNone) return fail(ctx, B2D_ERR_STATE, "peer %d already imported", peer);
+  HandleBlob b;
+  memcpy(&b, handle_buf, sizeof(b));
+  if (b.magic != kMagic || b.version != B2D_VERSION) return fail(ctx, B2D_ERR_INVALID, "handle magic/version mismatch");
+  if (b.rank != peer || b.world != ctx->world) return fail(ctx, B2D_ERR_INVALID, "handle is from rank %d/%d, expected %d/%d", b.rank, b.world, peer, ctx->world);
+  if (b.arena_bytes != ctx->arena_bytes) return fail(ctx, B2D_ERR_INVALID, "peer arena is %llu bytes, ours %zu: arenas must be symmetric", (unsigned long long)b.arena_bytes, ctx->arena_bytes);
+  if (b.mem_kind != ctx->mem_kind) return fail(ctx, B2D_ERR_INVALID, "peer memory kind differs");
+  DeviceGuard guard(ctx->device);
+  unsigned char* mapped = nullptr;
+  if (b.pid == static_cast<int64_t>(getpid())) {
+    // another rank of this very process (loopback ranks / single-process multi-GPU)
+    mapped = reinterpret_cast<unsigned char*>(b.arena_ptr);
+    if (b.device != ctx->device) {
+      if (ctx->mem_kind == 1) {
+        CUmemAccessDesc desc{};
+        desc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        desc.location.id = ctx->device;
+        desc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        B2D_CU(ctx, g_drv.MemSetAccess(reinterpret_cast<CUdeviceptr>(mapped), b.arena_bytes, &desc, 1));
+      } else {
+        int can = 0;
+        B2D_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, b.device));
+        if (!can) return fail(ctx, B2D_ERR_PEER, "device %d cannot access device %d", ctx->device, b.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+          return fail(ctx, B2D_ERR_PEER, "cudaDeviceEnablePeerAccess(%d) failed: %s", b.device, cudaGetErrorString(e));
+        }
+        cudaGetLastError();
+      }
+    }
+    ctx->peer_map[peer] = kMapDirect;
+  } else if (ctx->mem_kind == 1) {
+    if (b.fd < 0) return fail(ctx, B2D_ERR_INVALID, "VMM handle of peer %d carries no fd (pass it with SCM_RIGHTS, then b2d_handle_set_fd)", peer);
+    CUmemGenericAllocationHandle h = 0;
+    B2D_CU(ctx, g_drv.MemImportFromShareableHandle(&h, reinterpret_cast<void*>(static_cast<uintptr_t>(b.fd)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    int rc = vmm_map(ctx, h, b.arena_bytes, ctx->device, &mapped);
+    if (rc != B2D_OK) { g_drv.MemRelease(h); return rc; }
+    ctx->peer_vmm[peer] = h;
+    ctx->peer_map[peer] = kMapVmm;
+  } else {
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, B2D_ERR_PEER, "cudaIpcOpenMemHandle(peer %d) failed: %s", peer, cudaGetErrorString(e));
+    }
+    mapped = static_cast<unsigned char*>(p);
+    ctx->peer_map[peer] = kMapLegacyIpc;
+  }
+  ctx->peers.arena[peer] = mapped;
+  ctx->peers.signal[peer] = reinterpret_cast<Signal*>(mapped);
+  return B2D_OK;
+}
+
+int b2d_ctx_finalize(b2d_ctx* ctx) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  for (int r = 0; r < ctx->world; ++r)
+    if (ctx->peer_map[r] == kMapNone) return fail(ctx, B2D_ERR_STATE, "peer %d has not been imported", r);
+  ctx->finalized = true;
+  return B2D_OK;
+}
+
+// ---- NVLS -------------------------------------------------------------------------------
+int b2d_mc_supported(b2d_ctx* ctx, int* supported) {
+  if (ctx == nullptr || supported == nullptr) return fail(ctx, B2D_ERR_INVALID, "NULL argument");
+  *supported = 0;
+  if (ctx->mem_kind != 1 || !driver_ready() || g_drv.MulticastCreate == nullptr) return B2D_OK;
+  CUdevice dev;
+  if (g_drv.DeviceGet(&dev, ctx->device) != CUDA_SUCCESS) return B2D_OK;
+  int v = 0;
+  if (g_drv.DeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) == CUDA_SUCCESS) *supported = v;
+  return B2D_OK;
+}
+
+int b2d_mc_create(b2d_ctx* ctx, int* fd_out) {
+  if (ctx == nullptr || fd_out == nullptr) return fail(ctx, B2D_ERR_INVALID, "NULL argument");
+  int sup = 0;
+  b2d_mc_supported(ctx, &sup);
+  if (!sup) return fail(ctx, B2D_ERR_UNSUPPORTED, "multicast not supported (needs B2D_FLAG_MEM_VMM and an NVSwitch fabric)");
+  DeviceGuard guard(ctx->device);
+  CUmulticastObjectProp mp{};
+  mp.numDevices = ctx->world;
+  mp.size = ctx->arena_bytes;
+  mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  CUmemGenericAllocationHandle mc = 0;
+  CUresult r = g_drv.MulticastCreate(&mc, &mp);
+  if (r != CUDA_SUCCESS) return fail(ctx, B2D_ERR_UNSUPPORTED, "cuMulticastCreate failed: %s", cu_err(r));
+  int fd = -1;
+  r = g_drv.MemExportToShareableHandle(&fd, mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+  if (r != CUDA_SUCCESS) { g_drv.MemRelease(mc); return fail(ctx, B2D_ERR_CUDA, "multicast export failed: %s", cu_err(r)); }
+  ctx->mc_handle = mc;
+  ctx->mc_size = ctx->arena_bytes;
+  *fd_out = fd;
+  return B2D_OK;
+}
+
+int b2d_mc_join(b2d_ctx* ctx, int fd) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  if (ctx->mem_kind != 1 || !driver_ready() || g_drv.MulticastCreate == nullptr) return fail(ctx, B2D_ERR_UNSUPPORTED, "multicast unavailable");
+  DeviceGuard guard(ctx->device);
+  if (ctx->mc_handle == 0) {
+    CUmemGenericAllocationHandle mc = 0;
+    B2D_CU(ctx, g_drv.MemImportFromShareableHandle(&mc, reinterpret_cast<void*>(static_cast<uintptr_t>(fd)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    ctx->mc_handle = mc;
+    ctx->mc_size = ctx->arena_bytes;
+  }
+  CUdevice dev;
+  B2D_CU(ctx, g_drv.DeviceGet(&dev, ctx->device));
+  B2D_CU(ctx, g_drv.MulticastAddDevice(ctx->mc_handle, dev));
+  ctx->mc_joined = true;
+  return B2D_OK;
+}
+
+int b2d_mc_bind(b2d_ctx* ctx) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  if (!ctx->mc_joined) return fail(ctx, B2D_ERR_STATE, "b2d_mc_join() first");
+  DeviceGuard guard(ctx->device);
+  B2D_CU(ctx, g_drv.MulticastBindMem(ctx->mc_handle, 0, ctx->vmm_handle, 0, ctx->arena_bytes, 0));
+  unsigned char* va = nullptr;
+  int rc = vmm_map(ctx, ctx->mc_handle, ctx->arena_bytes, ctx->device, &va);
+  if (rc != B2D_OK) return rc;
+  ctx->peers.mc_arena = va;
+  ctx->mc_bound = true;
+  return B2D_OK;
+}
+
+int b2d_ctx_destroy(b2d_ctx* ctx) {
+  if (ctx == nullptr) return B2D_OK;
+  {
+    DeviceGuard guard(ctx->device);
+    cudaDeviceSynchronize();
+    cudaGetLastError();
+    for (auto& pr : ctx->ev_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& e : ctx->wait_ev) if (e != nullptr) cudaEventDestroy(e);
+    if (ctx->peers.mc_arena != nullptr) vmm_unmap(ctx->peers.mc_arena, ctx->arena_bytes);
+    if (ctx->mc_handle != 0) {
+      if (ctx->mc_bound) {
+        CUdevice dev;
+        if (g_drv.DeviceGet(&dev, ctx->device) == CUDA_SUCCESS) g_drv.MulticastUnbind(ctx->mc_handle, dev, 0, ctx->arena_bytes);
+      }
+      g_drv.MemRelease(ctx->mc_handle);
+    }
+    for (int r = 0; r < ctx->world; ++r) {
+      if (ctx->peer_map[r] == kMapLegacyIpc) cudaIpcCloseMemHandle(ctx->peers.arena[r]);
+      if (ctx->peer_map[r] == kMapVmm) { vmm_unmap(ctx->peers.arena[r], ctx->arena_bytes); g_drv.MemRelease(ctx->peer_vmm[r]); }
+    }
+    if (ctx->arena != nullptr) {
+      if (ctx->mem_kind == 1) { vmm_unmap(ctx->arena, ctx->arena_bytes); }
+      else cudaFree(ctx->arena);
+    }
+    if (ctx->vmm_handle != 0) g_drv.MemRelease(ctx->vmm_handle);
+    if (ctx->own_fd >= 0) close(ctx->own_fd);
+    if (ctx->diag_host != nullptr) cudaFreeHost(ctx->diag_host);
+    cudaGetLastError();
+  }
+  delete ctx;
+  return B2D_OK;
+}
+
+// ---- knobs -------------------------------------------------------------------------------
+int b2d_ctx_set_timeout(b2d_ctx* ctx, unsigned timeout_ms) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  ctx->timeout_ms = timeout_ms;
+  return B2D_OK;
+}
+int b2d_ctx_set_max_ctas(b2d_ctx* ctx, int max_ctas) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  if (max_ctas < 1 || max_ctas > B2D_MAX_BLOCKS) return fail(ctx, B2D_ERR_INVALID, "max_ctas must be in [1, %d]", B2D_MAX_BLOCKS);
+  ctx->max_ctas = max_ctas;
+  return B2D_OK;
+}
+int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  ctx->one_shot_max_bytes = wire_bytes;
+  return B2D_OK;
+}
+
+int b2d_plan(b2d_ctx* ctx, size_t n, int wire, int algo, int* algo_out, int* grid_out, int* block_out) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  if (wire != B2D_WIRE_FP32 && wire != B2D_WIRE_BF16) return fail(ctx, B2D_ERR_INVALID, "bad wire %d", wire);
+  const int a = pick_algo(ctx, n, wire, algo);
+  int grid;
+  if (ctx->world == 1) {
+    size_t g = (n / 4 + static_cast<size_t>(kThreads) * 4 - 1) / (static_cast<size_t>(kThreads) * 4);
+    const size_t cap = static_cast<size_t>(ctx->sm_count) * 4;
+    grid = static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+  } else {
+    grid = pick_grid(ctx, n, wire, a);
+  }
+  if (algo_out) *algo_out = a;
+  if (grid_out) *grid_out = grid;
+  if (block_out) *block_out = kThreads;
+  return B2D_OK;
+}
+
+// ---- data path ---------------------------------------------------------------------------
+int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, int wire, float scale,
+                         int algo, void* wait_stream, void* comm_stream) {
+  int rc = check_ready(ctx);
+  if (rc != B2D_OK) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (grad == nullptr && n != 0) return fail(ctx, B2D_ERR_INVALID, "grad is NULL");
+  if (reinterpret_cast<uintptr_t>(grad) % 16 != 0) return fail(ctx, B2D_ERR_INVALID, "bucket buffer must be 16-byte aligned");
+  if (wire != B2D_WIRE_FP32 && wire != B2D_WIRE_BF16) return fail(ctx, B2D_ERR_INVALID, "bad wire %d", wire);
+  if (algo < B2D_ALGO_AUTO || algo > B2D_ALGO_NVLS) return fail(ctx, B2D_ERR_INVALID, "bad algo %d", algo);
+  if (algo == B2D_ALGO_NVLS && !ctx->mc_bound && ctx->world > 1) return fail(ctx, B2D_ERR_UNSUPPORTED, "NVLS requested but no multicast object is bound");
+  if (n == 0) return B2D_OK;  // empty bucket: nothing to exchange, and every rank agrees on that
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(ctx, B2D_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->device);
+  cudaStream_t comm = static_cast<cudaStream_t>(comm_stream);
+
+  int a = 0, grid = 0;
+  b2d_plan(ctx, n, wire, algo, &a, &grid, nullptr);
+
+  if (ctx->world == 1) {
+    LaunchScope ls{ctx};
+    rc = ls.begin(wait_stream, comm_stream);
+    if (rc != B2D_OK) return rc;
+    if (wire == B2D_WIRE_BF16) k0_cast_scale_kernel<true><<<grid, kThreads, 0, comm>>>(grad, n, scale);
+    else k0_cast_scale_kernel<false><<<grid, kThreads, 0, comm>>>(grad, n, scale);
+    ctx->last_algo = 0; ctx->last_grid = grid; ctx->last_block = kThreads;
+    return ls.end();
+  }
+
+  const size_t epp = wire == B2D_WIRE_BF16 ? 8 : 4;
+  const size_t npacks = (n + epp - 1) / epp;
+  const size_t slice = (npacks + ctx->world - 1) / ctx->world;
+  const size_t half = slice * ctx->world * 16;
+  size_t stage_off = 0;
+  rc = get_slot(ctx, bucket_idx, half, n, wire, a, grid, comm, &stage_off);
+  if (rc != B2D_OK) return rc;
+
+  ArParams P = make_ar_params(ctx);
+  P.grad = grad; P.n = n; P.stage_off = stage_off; P.scale = scale;
+  LaunchScope ls{ctx};
+  rc = ls.begin(wait_stream, comm_stream);
+  if (rc != B2D_OK) return rc;
+  const bool bf = wire == B2D_WIRE_BF16;
+  switch (a) {
+    case B2D_ALGO_ONE_SHOT:
+      if (bf) launch_one_shot<true>(P, ctx->world, grid, comm); else launch_one_shot<false>(P, ctx->world, grid, comm);
+      break;
+    case B2D_ALGO_TWO_SHOT:
+      if (bf) launch_two_shot<true, false>(P, ctx->world, grid, comm); else launch_two_shot<false, false>(P, ctx->world, grid, comm);
+      break;
+    case B2D_ALGO_NVLS:
+      if (bf) launch_two_shot<true, true>(P, ctx->world, grid, comm); else launch_two_shot<false, true>(P, ctx->world, grid, comm);
+      break;
+    default:
+      return fail(ctx, B2D_ERR_INVALID, "bad algo %d", a);
+  }
+  ctx->last_algo = a; ctx->last_grid = grid; ctx->last_block = kThreads;
+  return ls.end();
+}
+
+static int sharded_common(b2d_ctx* ctx, int slot, const float* grads, float* params, float* exp_avg,
+                          float* exp_avg_sq, float* rs_out, size_t n, const int64_t* shard_off, int wire,
+                          float scale, const b2d_adam* adam, int do_sr, int do_gather, int end_barrier,
+                          void* wait_stream, void* comm_stream) {
+  int rc = check_ready(ctx);
+  if (rc != B2D_OK) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (shard_off == nullptr) return fail(ctx, B2D_ERR_INVALID, "shard_off is NULL");
+  if (wire != B2D_WIRE_FP32 && wire != B2D_WIRE_BF16) return fail(ctx, B2D_ERR_INVALID, "bad wire %d", wire);
+  if (shard_off[0] != 0 || static_cast<size_t>(shard_off[ctx->world]) != n)
+    return fail(ctx, B2D_ERR_INVALID, "shard_off must start at 0 and end at n");
+  size_t max_len = 0;
+  for (int r = 0; r < ctx->world; ++r) {
+    if (shard_off[r + 1] < shard_off[r] || shard_off[r] % 8 != 0 || shard_off[r + 1] % 8 != 0)
+      return fail(ctx, B2D_ERR_INVALID, "shard offsets must be non-decreasing multiples of 8 (got %lld..%lld for rank %d)",
+                  (long long)shard_off[r], (long long)shard_off[r + 1], r);
+    const size_t l = static_cast<size_t>(shard_off[r + 1] - shard_off[r]);
+    max_len = l > max_len ? l : max_len;
+  }
+  if (n == 0) return B2D_OK;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(ctx, B2D_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->device);
+  cudaStream_t comm = static_cast<cudaStream_t>(comm_stream);
+
+  ShParams P{};
+  P.grads = grads; P.params = params; P.exp_avg = exp_avg; P.exp_avg_sq = exp_avg_sq; P.rs_out = rs_out;
+  P.n = n; P.scale = scale; P.rank = ctx->rank; P.world = ctx->world;
+  P.do_stage_reduce = do_sr; P.do_adam = adam != nullptr; P.do_gather = do_gather; P.end_barrier = end_barrier;
+  for (int r = 0; r <= ctx->world; ++r) P.off[r] = shard_off[r];
+  for (int r = ctx->world + 1; r <= B2D_MAX_WORLD; ++r) P.off[r] = shard_off[ctx->world];
+  P.timeout_ns = static_cast<unsigned long long>(ctx->timeout_ms) * 1000000ull;
+  P.diag = ctx->diag_dev; P.peers = ctx->peers;
+
+  if (do_gather) {
+    const unsigned char* p8 = reinterpret_cast<const unsigned char*>(params);
+    if (p8 < ctx->arena || p8 + n * 4 > ctx->arena + ctx->arena_bytes)
+      return fail(ctx, B2D_ERR_INVALID, "the flat parameter buffer must live in the symmetric arena (b2d_arena_alloc)");
+    P.param_off = static_cast<size_t>(p8 - ctx->arena);
+  }
+  if (do_sr) {
+    if (grads == nullptr || reinterpret_cast<uintptr_t>(grads) % 16 != 0) return fail(ctx, B2D_ERR_INVALID, "grads must be a 16-byte aligned device pointer");
+    if (adam != nullptr) {
+      if (params == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr) return fail(ctx, B2D_ERR_INVALID, "params/exp_avg/exp_avg_sq are NULL");
+      if (adam->step < 1) return fail(ctx, B2D_ERR_INVALID, "adam.step must be >= 1");
+      AdamConsts& a = P.adam;
+      a.lr = adam->lr; a.beta1 = adam->beta1; a.beta2 = adam->beta2; a.eps = adam->eps; a.weight_decay = adam->weight_decay;
+      a.one_minus_beta1 = static_cast<float>(1.0 - static_cast<double>(adam->beta1));
+      a.one_minus_beta2 = static_cast<float>(1.0 - static_cast<double>(adam->beta2));
+      // python-float (double) arithmetic of torch/optim/adam.py:503-541, cast once
+      double bc1 = 1.0, bc2 = 1.0, b1p = 1.0, b2p = 1.0;
+      for (int i = 0; i < adam->step; ++i) { b1p *= static_cast<double>(adam->beta1); b2p *= static_cast<double>(adam->beta2); }
+      bc1 = 1.0 - b1p; bc2 = 1.0 - b2p;
+      a.step_size = static_cast<float>(static_cast<double>(adam->lr) / bc1);
+      a.inv_bc2_sqrt = 1.0f / static_cast<float>(sqrt(bc2));
+      a.decay_mul = static_cast<float>(1.0 - static_cast<double>(adam->lr) * static_cast<double>(adam->weight_decay));
+      a.adamw = adam->adamw;
+      if (adam->zero_grads) P.grads_rw = const_cast<float*>(grads);
+    } else if (rs_out == nullptr) {
+      return fail(ctx, B2D_ERR_INVALID, "reduce-scatter output is NULL");
+    }
+    const size_t half = n * (wire == B2D_WIRE_BF16 ? 2 : 4);
+    size_t work = max_len / (wire == B2D_WIRE_BF16 ? 8 : 4);
+    size_t grid = (work + kThreads - 1) / kThreads;
+    if (grid < 1) grid = 1;
+    if (grid > static_cast<size_t>(ctx->max_ctas)) grid = ctx->max_ctas;
+    size_t stage_off = 0;
+    rc = get_slot(ctx, 0x40000000 + slot, half, n, wire, 100 + do_gather, static_cast<int>(grid), comm, &stage_off);
+    if (rc != B2D_OK) return rc;
+    P.stage_off = stage_off;
+    LaunchScope ls{ctx};
+    rc = ls.begin(wait_stream, comm_stream);
+    if (rc != B2D_OK) return rc;
+    if (wire == B2D_WIRE_BF16) launch_sharded<true>(P, ctx->world, static_cast<int>(grid), comm);
+    else launch_sharded<false>(P, ctx->world, static_cast<int>(grid), comm);
+    ctx->last_algo = 10; ctx->last_grid = static_cast<int>(grid); ctx->last_block = kThreads;
+    return ls.end();
+  }
+  // all-gather only
+  size_t grid = (max_len / 4 + kThreads - 1) / kThreads;
+  if (grid < 1) grid = 1;
+  if (grid > static_cast<size_t>(ctx->max_ctas)) grid = ctx->max_ctas;
+  LaunchScope ls{ctx};
+  rc = ls.begin(wait_stream, comm_stream);
+  if (rc != B2D_OK) return rc;
+  launch_sharded<false>(P, ctx->world, static_cast<int>(grid), comm);
+  ctx->last_algo = 11; ctx->last_grid = static_cast<int>(grid); ctx->last_block = kThreads;
+  return ls.end();
+}
+
+int b2d_sharded_step(b2d_ctx* ctx, int slot, const float* grads, float* params, float* exp_avg,
+                     float* exp_avg_sq, size_t n, const int64_t* shard_off, int wire, float scale,
+                     const b2d_adam* adam, void* wait_stream, void* comm_stream) {
+  if (adam == nullptr) return fail(ctx, B2D_ERR_INVALID, "adam is NULL");
+  return sharded_common(ctx, slot, grads, params, exp_avg, exp_avg_sq, nullptr, n, shard_off, wire, scale, adam,
+                        1, 1, 0, wait_stream, comm_stream);
+}
+
+int b2d_reduce_scatter(b2d_ctx* ctx, int slot, const float* grads, float* out, size_t n,
+                       const int64_t* shard_off, int wire, float scale, void* wait_stream, void* comm_stream) {
+  return sharded_common(ctx, slot, grads, nullptr, nullptr, nullptr, out, n, shard_off, wire, scale, nullptr,
+                        1, 0, 0, wait_stream, comm_stream);
+}
+
+int b2d_allgather(b2d_ctx* ctx, float* buf, size_t n, const int64_t* shard_off, void* wait_stream, void* comm_stream) {
+  return sharded_common(ctx, 0, nullptr, buf, nullptr, nullptr, nullptr, n, shard_off, B2D_WIRE_FP32, 1.f, nullptr,
+                        0, 1, 1, wait_stream, comm_stream);
+}
+
+int b2d_barrier(b2d_ctx* ctx, void* stream) {
+  int rc = check_ready(ctx);
+  if (rc != B2D_OK) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (ctx->world == 1) return B2D_OK;
+  DeviceGuard guard(ctx->device);
+  return launch_barrier(ctx, static_cast<cudaStream_t>(stream));
+}
+
+// ---- arena -------------------------------------------------------------------------------
+int b2d_arena_alloc(b2d_ctx* ctx, size_t bytes, void** dev_ptr, size_t* offset) {
+  if (ctx == nullptr || dev_ptr == nullptr) return fail(ctx, B2D_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  bytes = round_up(bytes, kAlign);
+  if (bytes > ctx->user_bottom || ctx->user_bottom - bytes < ctx->slot_top)
+    return fail(ctx, B2D_ERR_NOMEM, "symmetric arena exhausted: %zu bytes requested, %zu free", bytes, ctx->user_bottom - ctx->slot_top);
+  ctx->user_bottom -= bytes;
+  *dev_ptr = ctx->arena + ctx->user_bottom;
+  if (offset) *offset = ctx->user_bottom;
+  return B2D_OK;
+}
+
+int b2d_arena_reset(b2d_ctx* ctx) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->slots.clear();
+  ctx->slot_top = kSignalBytes;
+  ctx->user_bottom = ctx->arena_bytes;
+  return B2D_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------
+int b2d_ctx_stats(b2d_ctx* ctx, b2d_stats* out) {
+  if (ctx == nullptr || out == nullptr) return fail(ctx, B2D_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  {
+    DeviceGuard guard(ctx->device);
+    resolve_timing(ctx, false);
+  }
+  memset(out, 0, sizeof(*out));
+  out->launches = ctx->launches;
+  out->timed_launches = ctx->timed_launches;
+  out->timed_ms = ctx->timed_ms;
+  out->arena_bytes = ctx->arena_bytes;
+  out->arena_used = (ctx->slot_top) + (ctx->arena_bytes - ctx->user_bottom);
+  out->world = ctx->world; out->rank = ctx->rank; out->device = ctx->device; out->sm_count = ctx->sm_count;
+  out->mem_kind = ctx->mem_kind; out->mc_bound = ctx->mc_bound ? 1 : 0;
+  out->last_algo = ctx->last_algo; out->last_grid = ctx->last_grid; out->last_block = ctx->last_block;
+  return B2D_OK;
+}
+
+int b2d_ctx_reset_stats(b2d_ctx* ctx) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  {
+    DeviceGuard guard(ctx->device);
+    resolve_timing(ctx, true);
+  }
+  ctx->launches = 0; ctx->timed_launches = 0; ctx->timed_ms = 0.0;
+  return B2D_OK;
+}
+
+}  // extern "C"
