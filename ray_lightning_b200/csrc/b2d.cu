@@ -406,6 +406,34 @@ void launch_sharded(const ShParams& P, int world, int grid, cudaStream_t st) {
   }
 }
 
+// CUDA loads kernels lazily; a load can serialise against running work, and these kernels spin on
+// peers.  Load every instantiation up front (what NCCL does at communicator init).
+template <typename K>
+void preload_one(K kernel) {
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess) cudaGetLastError();
+}
+template <int W>
+void preload_world() {
+  preload_one(k1_one_shot_kernel<W, true>);
+  preload_one(k1_one_shot_kernel<W, false>);
+  preload_one(k2_two_shot_kernel<W, true, false>);
+  preload_one(k2_two_shot_kernel<W, false, false>);
+  preload_one(k2_two_shot_kernel<W, true, true>);
+  preload_one(k2_two_shot_kernel<W, false, true>);
+  preload_one(k456_sharded_kernel<W, true>);
+  preload_one(k456_sharded_kernel<W, false>);
+}
+void preload_kernels() {
+  preload_one(k0_cast_scale_kernel<true>);
+  preload_one(k0_cast_scale_kernel<false>);
+  preload_one(barrier_kernel);
+  preload_world<0>();
+  preload_world<2>();
+  preload_world<4>();
+  preload_world<8>();
+}
+
 int check_ready(b2d_ctx* ctx) {
   if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
   if (!ctx->finalized) return fail(ctx, B2D_ERR_STATE, "b2d_ctx_finalize() has not been called");
@@ -517,6 +545,7 @@ int b2d_ctx_create(int rank, int world, int device, size_t arena_bytes, unsigned
     cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     if (r != cudaSuccess) { cudaGetLastError(); return bail(fail(ctx, B2D_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(r))); }
   }
+  preload_kernels();
   if (world == 1) ctx->finalized = true;
   *out = ctx;
   return B2D_OK;

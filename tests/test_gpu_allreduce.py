@@ -1,0 +1,196 @@
+"""Parity of the CUDA allreduce path (K0/K1/K2) against the oracle, through the C ABI.
+
+Every test drives libb2d exactly as the DDP hook does (b2d_allreduce_bucket on flat fp32 buckets).
+Multi-rank cases run W "loopback" ranks on the one GPU of the test box: separate contexts, arenas,
+signal pads and streams — the complete inter-rank protocol, minus the NVLink wires.
+Bar: bit-exact against oracle.ddp_oracle (both wires); golden fixtures from the reference's own
+torch-DDP run reproduced bit-exactly at W=2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ddp_oracle
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [1, 7, 8, 9, 1000, 4099, 65536 + 3, (1 << 20) + 5]
+_groups = {}
+
+
+def group(world):
+    from ray_lightning_b200.comm import LoopbackGroup
+    if world not in _groups:
+        _groups[world] = LoopbackGroup(world, 0, arena_bytes=768 << 20, timeout_ms=20000)
+    return _groups[world]
+
+
+def teardown_module(module):
+    for g in _groups.values():
+        g.close()
+    _groups.clear()
+
+
+def rank_inputs(world, n, seed=0, scale_pow=-4):
+    out = []
+    for r in range(world):
+        gen = torch.Generator().manual_seed(1234 + r + 1000 * seed)
+        out.append(torch.randn(n, generator=gen) * 2.0 ** scale_pow)
+    return out
+
+
+def oracle(per_rank, wire):
+    fn = ddp_oracle.allreduce_bf16_wire if wire == "bf16" else ddp_oracle.allreduce_fp32_wire
+    return fn(per_rank)
+
+
+def same_bits(a, b):
+    a = a.detach().cpu().contiguous().view(torch.int32)
+    b = b.detach().cpu().contiguous().view(torch.int32)
+    return torch.equal(a, b)
+
+
+def run(world, per_rank, wire, algo, bucket_idx):
+    g = group(world)
+    bufs = [t.cuda() for t in per_rank]
+    g.allreduce_(bufs, bucket_idx=bucket_idx, wire=wire, algo=algo)
+    g.synchronize()
+    return bufs
+
+
+@pytest.mark.parametrize("wire", ["bf16", "fp32"])
+def test_k0_world1_is_the_cast_roundtrip(wire):
+    from ray_lightning_b200 import _b2d
+    ctx = _b2d.Context(0, 1, 0, 1 << 20)
+    try:
+        for n in SIZES:
+            x = rank_inputs(1, n)[0]
+            buf = x.cuda()
+            st = torch.cuda.current_stream()
+            ctx.allreduce_bucket(0, buf.data_ptr(), n, _b2d.WIRE_NAMES[wire], 1.0, 0, st, st)
+            torch.cuda.synchronize()
+            assert same_bits(buf, oracle([x], wire)), (wire, n)
+            if wire == "bf16":  # and it is what torch's own hook prologue+epilogue computes on this GPU
+                ref = x.cuda().to(torch.bfloat16).div_(1).to(torch.float32)
+                assert same_bits(buf, ref)
+        assert ctx.stats()["launches"] == len(SIZES)
+    finally:
+        ctx.destroy()
+
+
+@pytest.mark.parametrize("world", [3, 6])
+def test_wire_value_matches_torch_cuda_division(world):
+    """The oracle's claim about `buffer.to(bf16).div_(W)` on CUDA (multiply by fp32 reciprocal)."""
+    x = rank_inputs(1, 100003)[0]
+    ref = x.cuda().to(torch.bfloat16).div_(world).to(torch.float32).cpu()
+    mine = ddp_oracle.wire_bf16(x, float(np.float32(1.0) / np.float32(world)))
+    assert same_bits(ref, mine)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("wire", ["bf16", "fp32"])
+@pytest.mark.parametrize("algo", ["one_shot", "two_shot"])
+def test_allreduce_bit_exact_vs_oracle(world, wire, algo):
+    for k, n in enumerate(SIZES):
+        per_rank = rank_inputs(world, n, seed=k)
+        want = oracle(per_rank, wire)
+        idx = 100 * k + (10 if wire == "bf16" else 20) + (1 if algo == "one_shot" else 2)
+        bufs = run(world, per_rank, wire, algo, idx)
+        for r in range(world):
+            assert same_bits(bufs[r], want), (world, wire, algo, n, r)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_auto_picks_one_shot_then_two_shot(world):
+    from ray_lightning_b200 import _b2d
+    g = group(world)
+    ctx = g.ranks[0].ctx
+    assert ctx.plan(1024, _b2d.WIRE_BF16)[0] == _b2d.ALGO_ONE_SHOT
+    assert ctx.plan(8 << 20, _b2d.WIRE_BF16)[0] == _b2d.ALGO_TWO_SHOT
+    per_rank = rank_inputs(world, 300001)
+    bufs = run(world, per_rank, "bf16", "auto", 7001)
+    assert same_bits(bufs[0], oracle(per_rank, "bf16"))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_special_values_propagate(world):
+    special = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan"), 1e-40, -1e-40, 3.3895e38,
+                            1.00390625, 1.005859375, 2.0 ** -126, 2.0 ** -133, 65504.0, -1.0])
+    per_rank = [torch.cat([special.roll(r), rank_inputs(world, 50)[r]]) for r in range(world)]
+    for wire in ("bf16", "fp32"):
+        for algo in ("one_shot", "two_shot"):
+            bufs = run(world, per_rank, wire, algo, 8000 + (wire == "bf16") * 2 + (algo == "one_shot"))
+            want = oracle(per_rank, wire)
+            got = bufs[0].cpu()
+            assert torch.equal(torch.isnan(got), torch.isnan(want))
+            ok = ~torch.isnan(want)
+            assert same_bits(got[ok], want[ok])
+
+
+@pytest.mark.parametrize("world,algo", [(2, "two_shot"), (4, "two_shot"), (8, "two_shot"), (4, "one_shot")])
+def test_back_to_back_steps_without_host_sync(world, algo):
+    """Five consecutive steps on the same bucket slot, launched back to back: exercises the double
+    buffering that replaces a trailing barrier."""
+    g = group(world)
+    n = 200003
+    steps = [rank_inputs(world, n, seed=50 + s) for s in range(5)]
+    bufs = [[t.cuda() for t in per_rank] for per_rank in steps]
+    torch.cuda.synchronize()
+    for s in range(5):
+        g.allreduce_(bufs[s], bucket_idx=9000 + world, wire="bf16", algo=algo)
+    g.synchronize()
+    for s in range(5):
+        want = oracle(steps[s], "bf16")
+        for r in range(world):
+            assert same_bits(bufs[s][r], want), (s, r)
+
+
+@pytest.mark.parametrize("name", ["small_mlp_w2", "mnist_w2"])
+def test_golden_fixtures_w2_bit_exact(name):
+    """Fixtures written by the reference's real path (torch DDP over gloo): same buckets in, same bits out."""
+    gold = load_golden(name)
+    for i in range(int(gold["n_buckets"])):
+        per_rank = [torch.from_numpy(gold["b%d_local_r%d" % (i, r)]) for r in range(2)]
+        bf = run(2, per_rank, "bf16", "auto", 9500 + i)
+        assert same_bits(bf[0], torch.from_numpy(gold["b%d_out_bf16_compress_hook" % i]))
+        assert same_bits(bf[1], bf[0])
+        fp = run(2, per_rank, "fp32", "auto", 9600 + i)
+        assert same_bits(fp[0], torch.from_numpy(gold["b%d_out_default" % i]))
+
+
+def test_golden_fixture_w4_within_tolerance():
+    gold = load_golden("small_mlp_w4")
+    for i in range(int(gold["n_buckets"])):
+        per_rank = [torch.from_numpy(gold["b%d_local_r%d" % (i, r)]) for r in range(4)]
+        fp = run(4, per_rank, "fp32", "two_shot", 9700 + i)
+        # north star: rtol 1e-3 / atol 1e-5 against the reference's fp32 DDP path
+        torch.testing.assert_close(fp[0].cpu(), torch.from_numpy(gold["b%d_out_default" % i]), rtol=1e-3, atol=1e-5)
+        bf = run(4, per_rank, "bf16", "two_shot", 9800 + i)
+        ref = torch.from_numpy(gold["b%d_out_bf16_compress_hook" % i]).double()
+        exact = ddp_oracle.allreduce_exact_f64(per_rank)
+        assert (bf[0].cpu().double() - exact).abs().max() <= (ref - exact).abs().max() + 1e-12
+
+
+@pytest.mark.parametrize("world", [8])
+def test_full_size_resnet50_bucket_properties(world):
+    """BASELINE config 2's largest bucket (30.04 MiB fp32 = 7 874 560 elements) at world 8: direct
+    oracle comparison plus size-independent properties."""
+    n = 7874560
+    per_rank = rank_inputs(world, n, seed=3)
+    bufs = run(world, per_rank, "bf16", "two_shot", 9900)
+    want = oracle(per_rank, "bf16")
+    for r in range(world):
+        assert same_bits(bufs[r], want)
+    out = bufs[0].clone()
+    # (1) results are bf16-representable: rounding again changes nothing
+    assert same_bits(out, out.to(torch.bfloat16).float())
+    # (2) linearity under exact (power-of-two) scaling
+    bufs2 = run(world, [t * 4.0 for t in per_rank], "bf16", "two_shot", 9900)
+    assert same_bits(bufs2[0], out * 4.0)
+    # (3) identical ranks, constant input: the mean is the constant
+    ones = [torch.full((n,), 0.5) for _ in range(world)]
+    bufs3 = run(world, ones, "bf16", "two_shot", 9900)
+    assert bool((bufs3[world - 1] == 0.5).all())
+    # (4) a checksum of checksums: sum of the output equals the oracle's, bit for bit in fp64
+    assert float(bufs[0].double().sum()) == float(want.double().sum())

@@ -1,0 +1,63 @@
+"""The one-process-per-GPU deployment (Ray-actor model) on whatever GPUs the box has: W worker
+processes, control plane over gloo, arenas shared through CUDA IPC (and VMM fds); when the box has
+fewer GPUs than ranks the ranks share cuda:0 — the IPC/handle/barrier path is the same."""
+import os
+import socket
+from contextlib import closing
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _port():
+    with closing(socket.socket(socket.AF_INET, socket.SOCK_STREAM)) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, mem, ret):
+    import numpy as np
+    import torch.distributed as dist
+    from oracle import ddp_oracle
+    from ray_lightning_b200.comm import Communicator
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="env://")
+    dev = rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    comm = Communicator(rank, world, dev, 128 << 20, mem=mem, timeout_ms=20000, max_ctas=128 // world, nvls="auto")
+    ok = True
+    try:
+        for k, n in enumerate([5, 4099, 1 << 20]):
+            per_rank = [torch.randn(n, generator=torch.Generator().manual_seed(77 + r + 10 * k)) * 0.05
+                        for r in range(world)]
+            for wire in ("bf16", "fp32"):
+                for algo in ("one_shot", "two_shot"):
+                    buf = per_rank[rank].cuda()
+                    comm.allreduce_(buf, bucket_idx=k * 10 + (wire == "bf16") * 2 + (algo == "one_shot"),
+                                    wire=wire, algo=algo)
+                    torch.cuda.synchronize()
+                    fn = ddp_oracle.allreduce_bf16_wire if wire == "bf16" else ddp_oracle.allreduce_fp32_wire
+                    want = fn(per_rank)
+                    ok = ok and torch.equal(buf.cpu().view(torch.int32), want.view(torch.int32))
+        st = comm.stats()
+        ret[rank] = {"ok": ok, "nvls": comm.nvls, "launches": st["launches"], "mem_kind": st["mem_kind"]}
+    finally:
+        comm.close()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mem", ["ipc", "vmm"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_worker_processes_share_arenas(world, mem):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _port(), mem, ret), nprocs=world, join=True)
+    assert sorted(ret.keys()) == list(range(world))
+    for r in range(world):
+        assert ret[r]["ok"], (r, dict(ret[r]))
+        assert ret[r]["launches"] == 12
+        assert ret[r]["mem_kind"] == (1 if mem == "vmm" else 0)

@@ -1,0 +1,120 @@
+"""Parity of the sharded path (K4 reduce-scatter to owner, K5 partitioned Adam, K6 parameter
+all-gather) against the oracle: torch.optim.Adam applied to the averaged gradients, which is what
+RayShardedStrategy's FairScale OSS computes in aggregate (ray_lightning/ray_ddp_sharded.py:12-13)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddp_oracle
+
+pytestmark = pytest.mark.gpu
+
+_groups = {}
+
+
+def group(world):
+    from ray_lightning_b200.comm import LoopbackGroup
+    if world not in _groups:
+        _groups[world] = LoopbackGroup(world, 0, arena_bytes=256 << 20, timeout_ms=20000)
+    return _groups[world]
+
+
+def teardown_module(module):
+    for g in _groups.values():
+        g.close()
+    _groups.clear()
+
+
+def layout(world, seed):
+    rng = np.random.default_rng(seed)
+    numels = [int(x) for x in rng.integers(1, 3000, size=37)] + [40000, 8, 1]
+    owner = ddp_oracle.partition_fairscale(numels, world)
+    offs, shard_off, total = ddp_oracle.shard_layout(numels, owner, world)
+    return numels, owner, offs, shard_off, total
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("wire", ["fp32", "bf16"])
+def test_reduce_scatter_bit_exact(world, wire):
+    g = group(world)
+    _, _, _, shard_off, total = layout(world, 1)
+    per_rank = [torch.randn(total, generator=torch.Generator().manual_seed(r)) * 0.1 for r in range(world)]
+    grads = [t.cuda() for t in per_rank]
+    outs = [torch.zeros(shard_off[r + 1] - shard_off[r], device="cuda") for r in range(world)]
+    g.reduce_scatter(grads, outs, shard_off, wire=wire, slot=1 + (wire == "bf16"))
+    g.synchronize()
+    scale = float(np.float32(1.0) / np.float32(world))
+    if wire == "fp32":
+        want = ddp_oracle.allreduce_fp32_wire(per_rank, scale)
+    else:  # bf16 wire, fp32 accumulate, NOT rounded again: the sum never goes back on the wire
+        want = None
+        for t in per_rank:
+            c = ddp_oracle.wire_bf16(t, scale)
+            want = c if want is None else want + c
+    for r in range(world):
+        assert torch.equal(outs[r].cpu(), want[shard_off[r]:shard_off[r + 1]]), (world, wire, r)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_allgather_bit_exact(world):
+    g = group(world)
+    _, _, _, shard_off, total = layout(world, 2)
+    full = torch.randn(total, generator=torch.Generator().manual_seed(5))
+    bufs = []
+    for r, rk in enumerate(g.ranks):
+        b = rk.arena_tensor(total)
+        b.zero_()
+        b[shard_off[r]:shard_off[r + 1]] = full[shard_off[r]:shard_off[r + 1]].cuda()
+        bufs.append(b)
+    torch.cuda.synchronize()
+    g.allgather_(bufs, shard_off)
+    g.synchronize()
+    for r in range(world):
+        assert torch.equal(bufs[r].cpu(), full), r
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("wire", ["fp32", "bf16"])
+@pytest.mark.parametrize("wd,adamw", [(0.0, False), (0.01, True)])
+def test_sharded_step_matches_adam_on_averaged_grads(world, wire, wd, adamw):
+    g = group(world)
+    _, _, _, shard_off, total = layout(world, 3)
+    p0 = torch.randn(total, generator=torch.Generator().manual_seed(11))
+    params, ms, vs = [], [], []
+    for r, rk in enumerate(g.ranks):
+        p = rk.arena_tensor(total)
+        p.copy_(p0.cuda())
+        params.append(p)
+        n_own = shard_off[r + 1] - shard_off[r]
+        ms.append(torch.zeros(n_own, device="cuda"))
+        vs.append(torch.zeros(n_own, device="cuda"))
+    ref_p = torch.nn.Parameter(p0.clone())
+    cls = torch.optim.AdamW if adamw else torch.optim.Adam
+    opt = cls([ref_p], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    scale = float(np.float32(1.0) / np.float32(world))
+    for step in range(1, 4):
+        per_rank = [torch.randn(total, generator=torch.Generator().manual_seed(100 * step + r)) * 0.1
+                    for r in range(world)]
+        grads = [t.cuda() for t in per_rank]
+        torch.cuda.synchronize()
+        g.sharded_step_(grads, params, ms, vs, shard_off, step=step, lr=1e-2, betas=(0.9, 0.999), eps=1e-8,
+                        weight_decay=wd, adamw=adamw, zero_grads=(step == 2), wire=wire, slot=10 + (wire == "bf16"))
+        g.synchronize()
+        if wire == "fp32":
+            avg = ddp_oracle.allreduce_fp32_wire(per_rank, scale)
+        else:
+            avg = sum(ddp_oracle.wire_bf16(t, scale) for t in per_rank)
+        ref_p.grad = avg.clone()
+        opt.step()
+        # every rank holds the same, whole parameter vector (bit-identical: it is a copy)
+        for r in range(1, world):
+            assert torch.equal(params[r], params[0]), (step, r)
+        torch.testing.assert_close(params[0].cpu(), ref_p.detach(), rtol=2e-5, atol=2e-6)
+        if step == 2:
+            assert all(float(gr.abs().max()) == 0.0 for gr in grads)
+    # optimizer state of the owned shard == the reference state of that slice
+    st = opt.state[ref_p]
+    for r in range(world):
+        sl = slice(shard_off[r], shard_off[r + 1])
+        torch.testing.assert_close(ms[r].cpu(), st["exp_avg"][sl], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(vs[r].cpu(), st["exp_avg_sq"][sl], rtol=1e-5, atol=1e-9)
