@@ -76,5 +76,88 @@ def loopback():
         g.close()
 
 
+def sweep():
+    """Real multi-GPU sweep (one process per GPU, launched by torchrun): libb2d vs NCCL."""
+    import torch.distributed as dist
+    from ray_lightning_b200.comm import Communicator
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mem = os.environ.get("B2D_MEM", "vmm")
+    max_ctas = int(os.environ.get("B2D_MAX_CTAS", "64"))
+    comm = Communicator(rank, world, local, 3 << 30, mem=mem, max_ctas=max_ctas, timeout_ms=20000, nvls="auto")
+    if rank == 0:
+        print(json.dumps({"bench": "sweep_setup", "world": world, "mem": mem, "nvls": comm.nvls, "max_ctas": max_ctas}), flush=True)
+    side = torch.cuda.Stream()
+    sizes = [64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20]  # bytes of WIRE payload (bf16)
+    iters = int(os.environ.get("B2D_ITERS", "30"))
+
+    def timed(fn, n_it):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_it):
+            fn()
+        b.record()
+        b.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / n_it], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    for wire_bytes in sizes:
+        n = wire_bytes // 2
+        buf = torch.randn(n, device="cuda") * 0.01
+        ref = buf.clone()
+        bus = 2 * (world - 1) / world * wire_bytes
+        rows = {}
+        algos = ["one_shot", "two_shot"] + (["nvls"] if comm.nvls else [])
+        for algo in algos:
+            if algo == "one_shot" and wire_bytes > (16 << 20):
+                continue
+            key = sizes.index(wire_bytes) * 10 + algos.index(algo)
+            f = lambda: comm.allreduce_(buf, bucket_idx=key, wire="bf16", algo=algo)
+            rows[algo] = timed(f, iters)
+        # the reference GPU path with the bf16 hook: cast+div, ncclAllReduce(bf16), copy back
+        def nccl_bf16():
+            c = buf.to(torch.bfloat16).div_(world)
+            dist.all_reduce(c)
+            buf.copy_(c)
+        rows["nccl_bf16_hook_seq"] = timed(nccl_bf16, iters)
+        cb = buf.to(torch.bfloat16)
+        rows["nccl_bf16_allreduce_only"] = timed(lambda: dist.all_reduce(cb), iters)
+        rows["nccl_fp32_allreduce"] = timed(lambda: dist.all_reduce(buf), iters)
+        buf.copy_(ref)
+        if rank == 0:
+            out = {"bench": "sweep", "world": world, "wire_bytes": wire_bytes, "n": n}
+            for k, ms in rows.items():
+                out[k + "_ms"] = round(ms, 4)
+                w = 4 * n if k == "nccl_fp32_allreduce" else wire_bytes
+                out[k + "_busGBps"] = round(2 * (world - 1) / world * w / ms / 1e6, 1)
+            print(json.dumps(out), flush=True)
+    # correctness against NCCL on the same inputs (fp32 wire: rtol 1e-3 / atol 1e-5)
+    g = torch.randn(1 << 20, device="cuda", generator=torch.Generator("cuda").manual_seed(rank))
+    mine = g.clone()
+    comm.allreduce_(mine, bucket_idx=999, wire="fp32", algo="two_shot")
+    theirs = g / world
+    dist.all_reduce(theirs)
+    torch.cuda.synchronize()
+    ok = torch.allclose(mine, theirs, rtol=1e-3, atol=1e-5)
+    mine2 = g.clone()
+    comm.allreduce_(mine2, bucket_idx=998, wire="bf16", algo="two_shot")
+    c = g.to(torch.bfloat16).div_(world)
+    dist.all_reduce(c)
+    torch.cuda.synchronize()
+    ok2 = torch.allclose(mine2, c.float(), rtol=2 ** -6, atol=1e-3)
+    if rank == 0:
+        print(json.dumps({"bench": "sweep_parity_vs_nccl", "fp32_allclose": bool(ok), "bf16_close": bool(ok2),
+                          "max_abs_diff_bf16": float((mine2 - c.float()).abs().max())}), flush=True)
+    comm.close()
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
-    {"k0": k0, "loopback": loopback}[sys.argv[1]]()
+    {"k0": k0, "loopback": loopback, "sweep": sweep}[sys.argv[1]]()
