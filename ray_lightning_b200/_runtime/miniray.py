@@ -144,6 +144,11 @@ class ObjectRef:
     def __init__(self, actor=None, call_id=None, value=None, ready=False):
         self._actor, self._call_id, self._value, self._ready, self._error = actor, call_id, value, ready, None
 
+    def __reduce__(self):
+        if self._ready and self._error is None:
+            return (put, (self._value,))
+        return (_stub, ())
+
     def _resolve(self, ok, payload):
         if ok:
             self._value = cloudpickle.loads(payload)
@@ -201,7 +206,22 @@ class _Method:
         return self._actor._submit(self._name, args, kwargs)
 
 
+class _RemoteHandleStub:
+    """What an ActorHandle / pending ObjectRef turns into when pickled into another process: actors
+    are driven from the driver only (the launcher pickles itself, handles included, to its workers)."""
+
+    def __getattr__(self, name):
+        raise RayActorError("actor handles are usable in the driver process only")
+
+
+def _stub():
+    return _RemoteHandleStub()
+
+
 class ActorHandle:
+    def __reduce__(self):
+        return (_stub, ())
+
     def __init__(self, cls, args, kwargs, req, gpu_ids):
         self._req, self._gpu_ids = req, gpu_ids
         self._ids = itertools.count(1)
