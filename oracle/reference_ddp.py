@@ -67,9 +67,9 @@ def make_model(name):
         return SmallMLP()
     if name == "mnist":
         return MNISTClassifier()
-    if name == "resnet50":
+    if name in ("resnet50", "resnet18"):
         import torchvision
-        return torchvision.models.resnet50()
+        return getattr(torchvision.models, name)()
     raise ValueError(name)
 
 
@@ -79,7 +79,7 @@ def make_batch(name, batch, seed):
         return torch.randn(batch, 37, generator=g), torch.randint(0, 11, (batch,), generator=g)
     if name == "mnist":
         return torch.rand(batch, 1, 28, 28, generator=g), torch.randint(0, 10, (batch,), generator=g)
-    if name == "resnet50":
+    if name in ("resnet50", "resnet18"):
         return torch.randn(batch, 3, 224, 224, generator=g), torch.randint(0, 1000, (batch,), generator=g)
     raise ValueError(name)
 

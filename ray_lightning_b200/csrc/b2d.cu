@@ -332,7 +332,8 @@ int pick_algo(b2d_ctx* ctx, size_t n, int wire, int algo) {
   if (ctx->world == 1) return B2D_ALGO_ONE_SHOT;
   if (algo != B2D_ALGO_AUTO) return algo;
   const size_t wire_bytes = n * (wire == B2D_WIRE_BF16 ? 2 : 4);
-  if (wire_bytes <= ctx->one_shot_max_bytes) return B2D_ALGO_ONE_SHOT;
+  // at world 2 one-shot moves exactly the two-shot's bytes with one barrier less
+  if (ctx->world == 2 || wire_bytes <= ctx->one_shot_max_bytes) return B2D_ALGO_ONE_SHOT;
   if (ctx->mc_bound) return B2D_ALGO_NVLS;
   return B2D_ALGO_TWO_SHOT;
 }

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_one_shot_kernel(const __grid_c
   uint4* my_stage = reinterpret_cast<uint4*>(P.peers.arena[P.rank] + P.stage_off);
 
   {
-    constexpr int B = BF16 ? 4 : 8;
+    constexpr int B = BF16 ? 8 : 16;  // 16 x 16-byte loads in flight per thread
     for (size_t j = g; j < npacks; j += gt * B) {
       size_t p[B];
       bool ok[B];
@@ -267,20 +267,25 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
   const size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   uint4* my_stage = reinterpret_cast<uint4*>(P.peers.arena[P.rank] + P.stage_off);
 
-  // phase 0: stage pack j of EVERY slice (peers' thread g will read exactly these)
+  // phase 0: stage pack j of EVERY slice (peers' thread g will read exactly these);
+  // UJ consecutive j per iteration so that 16 x 16-byte loads are in flight per thread
   {
-    constexpr int B = (W > 0) ? (BF16 ? (W > 4 ? 4 : W) : W) : 4;
-    for (size_t j = g; j < slice; j += gt) {
-      for (int s0 = 0; s0 < world; s0 += B) {
-        size_t p[B];
-        bool ok[B];
+    constexpr int LPP = BF16 ? 2 : 1;                       // 16-byte loads per pack
+    constexpr int UJ = (W > 0 && kMaxLoadsInFlight / (W * LPP) > 1) ? kMaxLoadsInFlight / (W * LPP) : 1;
+    constexpr int B = WW * UJ;
+    for (size_t j = g; j < slice; j += gt * UJ) {
+      size_t p[B];
+      bool ok[B];
 #pragma unroll
-        for (int i = 0; i < B; ++i) {
-          p[i] = static_cast<size_t>(s0 + i) * slice + j;
-          ok[i] = (s0 + i < world) && p[i] < npacks;
+      for (int u = 0; u < UJ; ++u) {
+#pragma unroll
+        for (int s = 0; s < WW; ++s) {
+          const size_t jj = j + u * gt;
+          p[u * WW + s] = static_cast<size_t>(s) * slice + jj;
+          ok[u * WW + s] = s < world && jj < slice && p[u * WW + s] < npacks;
         }
-        stage_batch<BF16, B>(P.grad, P.n, my_stage, p, ok, P.scale);
       }
+      stage_batch<BF16, B>(P.grad, P.n, my_stage, p, ok, P.scale);
     }
   }
   block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
@@ -337,30 +342,34 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
   }
   block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
 
-  // phase 2: all-gather + fp32 write-back
+  // phase 2: all-gather + fp32 write-back, again 16 loads in flight per thread
   {
-    constexpr int B = (W > 0) ? (W > 8 ? 8 : W) : 4;
-    for (size_t j = g; j < slice; j += gt) {
-      for (int s0 = 0; s0 < world; s0 += B) {
-        uint4 in[B];
+    constexpr int UJ = (W > 0 && kMaxLoadsInFlight / W > 1) ? kMaxLoadsInFlight / W : 1;
+    constexpr int B = WW * UJ;
+    for (size_t j = g; j < slice; j += gt * UJ) {
+      uint4 in[B];
+      size_t p[B];
+      bool ok[B];
 #pragma unroll
-        for (int i = 0; i < B; ++i) {
-          const int s = s0 + i;
-          const size_t p = static_cast<size_t>(s) * slice + j;
-          if (s < world && p < npacks) {
+      for (int u = 0; u < UJ; ++u) {
+#pragma unroll
+        for (int s = 0; s < WW; ++s) {
+          const int i = u * WW + s;
+          const size_t jj = j + u * gt;
+          p[i] = static_cast<size_t>(s) * slice + jj;
+          ok[i] = s < world && jj < slice && p[i] < npacks;
+          if (ok[i]) {
             const unsigned char* src = NVLS ? P.peers.arena[P.rank] : P.peers.arena[s];
-            in[i] = ld_peer_v4(reinterpret_cast<const uint4*>(src + P.stage_off) + p);
+            in[i] = ld_peer_v4(reinterpret_cast<const uint4*>(src + P.stage_off) + p[i]);
           }
         }
+      }
 #pragma unroll
-        for (int i = 0; i < B; ++i) {
-          const int s = s0 + i;
-          const size_t p = static_cast<size_t>(s) * slice + j;
-          if (s < world && p < npacks) {
-            uint4 raw[EPP / 4];
-            from_wire<BF16>(in[i], raw);
-            grad_store<EPP>(P.grad, P.n, p, raw);
-          }
+      for (int i = 0; i < B; ++i) {
+        if (ok[i]) {
+          uint4 raw[EPP / 4];
+          from_wire<BF16>(in[i], raw);
+          grad_store<EPP>(P.grad, P.n, p[i], raw);
         }
       }
     }
