@@ -38,15 +38,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 64 resnet, 16 bert, 4 gpt2)")
     ap.add_argument("--bucket-cap-mb", type=int, default=25)
     ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--mem", default="vmm", choices=["vmm", "ipc"])
     ap.add_argument("--max-ctas", type=int, default=None)
-    ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--model", default="resnet50", choices=["resnet50", "resnet18", "bert-base", "gpt2-medium"])
+    ap.add_argument("--strategy", default="ddp", choices=["ddp", "sharded"],
+                    help="ddp = RayStrategy; sharded = RayShardedStrategy (fused reduce-scatter + Adam + all-gather)")
+    ap.add_argument("--hook", default="b200", choices=["b200", "nccl_bf16", "nccl_fp32"],
+                    help="b200 = libb2d; nccl_* = the reference's GPU path through the same strategy (A/B)")
+    ap.add_argument("--seq", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=16)
+    ap.add_argument("--cpu-batch", type=int, default=8)
     return ap.parse_args()
 
 
@@ -103,11 +108,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores():
+    """Host threads this process can really run: affinity mask, capped by the cgroup CPU quota, and by
+    B2D_CPU_THREADS when set (oversubscribing a quota makes the CPU arm pathologically slow)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    cap = int(os.environ.get("B2D_CPU_THREADS", "64"))   # beyond ~64 threads torch's CPU conv backward stops scaling
+    return max(1, min(n, cap))
+
+
 # ---- the reference arm / cpu baseline: torch DDP over gloo on the host cores ---------------------
 def cpu_reference(world, batch, steps, warmup, model="resnet50"):
     """What RayStrategy(num_workers=world, use_gpu=False) executes in its workers (oracle/reference_ddp.py)."""
     from oracle import reference_ddp
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = usable_cores()
     cfg = {"model": model, "batch": batch, "steps": steps, "warmup": warmup, "threads_total": cores,
            "ddp_kwargs": {"find_unused_parameters": False, "gradient_as_bucket_view": True}}
     t0 = time.time()
@@ -168,48 +187,94 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
 
-    class Net(LightningModule):
-        def __init__(self):
-            super().__init__()
-            import torchvision
-            torch.manual_seed(0)
-            self.net = torchvision.models.resnet50() if args.model == "resnet50" else torchvision.models.resnet18()
+    import torchvision
+    torch.manual_seed(0)
+    if args.model.startswith("resnet"):
+        B = args.batch or 64
+        unit = "images"
 
-        def forward(self, x):
-            return self.net(x)
+        class Net(LightningModule):
+            def __init__(self):
+                super().__init__()
+                self.net = getattr(torchvision.models, args.model)()
 
-        def training_step(self, batch, batch_idx):
-            x, y = batch
-            return F.cross_entropy(self.net(x), y)
+            def training_step(self, batch, batch_idx):
+                x, y = batch
+                return F.cross_entropy(self.net(x), y)
 
-        def configure_optimizers(self):
-            return torch.optim.SGD(self.parameters(), lr=0.05, momentum=0.9)
+            def configure_optimizers(self):
+                return torch.optim.SGD(self.parameters(), lr=0.05, momentum=0.9)
+
+        def host_batch(g):
+            return (torch.randn(B, 3, 224, 224, generator=g).contiguous(memory_format=torch.channels_last),
+                    torch.randint(0, 1000, (B,), generator=g))
+    else:
+        import transformers
+        unit = "sequences"
+        if args.model == "bert-base":      # BASELINE.json configs[2]
+            B, S = args.batch or 16, args.seq or 512
+            cfg = transformers.BertConfig()
+            make = lambda: transformers.BertForMaskedLM(cfg)
+        else:                               # gpt2-medium, BASELINE.json configs[3]
+            B, S = args.batch or 4, args.seq or 1024
+            cfg = transformers.GPT2Config(n_embd=1024, n_layer=24, n_head=16)
+            make = lambda: transformers.GPT2LMHeadModel(cfg)
+        vocab = cfg.vocab_size
+
+        class Net(LightningModule):
+            def __init__(self):
+                super().__init__()
+                self.net = make()
+
+            def training_step(self, batch, batch_idx):
+                ids, = batch
+                return self.net(input_ids=ids, labels=ids).loss
+
+            def configure_optimizers(self):
+                return (torch.optim.Adam if args.strategy == "sharded" else torch.optim.AdamW)(self.parameters(), lr=1e-4)
+
+        def host_batch(g):
+            return (torch.randint(0, vocab, (B, S), generator=g),)
 
     # the worker-side call sequence of RayLauncher._wrapping_function (launchers/ray_launcher.py)
-    strategy = RayStrategy(num_workers=world, use_gpu=True, find_unused_parameters=False, gradient_as_bucket_view=True,
-                           bucket_cap_mb=args.bucket_cap_mb, b200_wire=args.wire, b200_algo=args.algo, b200_mem=args.mem,
-                           b200_timing=True, b200_max_ctas=args.max_ctas)
+    from ray_lightning_b200 import RayShardedStrategy
+    kw = dict(num_workers=world, use_gpu=True, b200_wire=args.wire, b200_algo=args.algo, b200_mem=args.mem,
+              b200_timing=True, b200_max_ctas=args.max_ctas)
+    if args.strategy == "sharded":
+        strategy = RayShardedStrategy(**kw)
+    else:
+        kw.update(find_unused_parameters=False, gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_cap_mb)
+        if args.hook != "b200":
+            kw["b200_enable"] = False
+            if args.hook == "nccl_bf16":
+                from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+                kw["ddp_comm_hook"] = default_hooks.bf16_compress_hook
+        strategy = RayStrategy(**kw)
     strategy.precision = "bf16"
     strategy.set_remote(True)
     strategy.set_global_to_local([(i, 0) for i in range(world)])
     strategy.root_device = dev
     strategy._worker_setup(process_idx=rank)
-    model = Net().to(memory_format=torch.channels_last)
+    model = Net()
+    if args.model.startswith("resnet"):
+        model = model.to(memory_format=torch.channels_last)
     strategy.connect(model)
     strategy.model_to_device()
     strategy.configure_ddp()
-    opt = model.configure_optimizers()
+
+    class _T:  # the two Trainer attributes setup_optimizers looks at
+        pass
+    strategy.setup_optimizers(_T())
+    opt = strategy.optimizers[0]
     n_params = sum(p.numel() for p in model.parameters())
 
-    B = args.batch
     g = torch.Generator().manual_seed(1000 + rank)
-    host_x = torch.randn(B, 3, 224, 224, generator=g).contiguous(memory_format=torch.channels_last).pin_memory()
-    host_y = torch.randint(0, 1000, (B,), generator=g).pin_memory()
-    dev_x, dev_y = host_x.to(dev, non_blocking=True), host_y.to(dev, non_blocking=True)
+    host = tuple(t.pin_memory() for t in host_batch(g))
+    devb = tuple(t.to(dev, non_blocking=True) for t in host)
 
-    def step(x, y, i):
-        opt.zero_grad(set_to_none=True)
-        loss = strategy.training_step((x, y), i)
+    def step(batch, i):
+        opt.zero_grad(set_to_none=True) if args.strategy == "ddp" else opt.zero_grad()
+        loss = strategy.training_step(batch, i)
         strategy.backward(loss)
         opt.step()
         return loss
@@ -226,11 +291,10 @@ def run_b200(args):
         last = None
         for i in range(n):
             if e2e:
-                x = host_x.to(dev, non_blocking=True)
-                y = host_y.to(dev, non_blocking=True)
-                last = float(step(x, y, i))  # device->host read of the step's result, every step
+                batch = tuple(t.to(dev, non_blocking=True) for t in host)
+                last = float(step(batch, i))  # device->host read of the step's result, every step
             else:
-                last = step(dev_x, dev_y, i)
+                last = step(devb, i)
         b.record()
         barrier()
         t = torch.tensor([a.elapsed_time(b)], device=dev)
@@ -239,11 +303,12 @@ def run_b200(args):
         return float(t), last
 
     for i in range(args.warmup):
-        step(dev_x, dev_y, i)
+        step(devb, i)
     barrier()
-    state = strategy.b200_state
-    comm = state.comm
-    comm.ctx.reset_stats()
+    state = strategy.b200_state if args.strategy == "ddp" else None
+    comm = state.comm if state is not None else getattr(strategy, "_comm", None)
+    if comm is not None:
+        comm.ctx.reset_stats()
     vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
     phys = int(vis[local]) if len(vis) > local and vis[local].isdigit() else local
     sampler = ClockSampler(phys)
@@ -252,7 +317,7 @@ def run_b200(args):
     total_ms, _ = timed(args.steps, e2e=False)
     clocks = sampler.stop() if rank == 0 else None
     torch.cuda.synchronize()
-    st = comm.stats()
+    st = comm.stats() if comm is not None else {"launches": 0, "timed_ms": 0.0, "timed_launches": 0}
     launches_timed, kernel_ms = int(st["launches"]), float(st["timed_ms"])
     timed_launches = int(st["timed_launches"])
     e2e_ms, last_loss = timed(args.steps, e2e=True)
@@ -268,10 +333,14 @@ def run_b200(args):
         if world == 1:
             # K0: 4 B read + 4 B write per gradient element, nothing else
             alg_bytes_step = 8.0 * n_params
+            if args.strategy == "sharded":   # stage (4 r + w w), reduce (w r), Adam p/m/v r+w + p (28), DESIGN.md §4
+                alg_bytes_step = (4.0 + 2 * wire_w + 28.0) * n_params
             bound, peak, unit = "hbm", float(peaks["hbm_gbs"]), "GB/s"
             peak_note = "MEASURED_PEAKS.json hbm_gbs (%s)" % peak_src
         else:
             alg_bytes_step = 2.0 * (world - 1) / world * n_params * wire_w   # NCCL-tests bus-bandwidth convention
+            if args.strategy == "sharded":   # reduce-scatter at wire width + fp32 parameter all-gather
+                alg_bytes_step = (world - 1) / world * n_params * (wire_w + 4.0)
             bound, peak, unit = "nvlink", NVLINK_PEAK_GBS, "GB/s"
             peak_note = "fallback: B200_PROFILING.md measured peer copy 770 GB/s per direction (not in MEASURED_PEAKS.json)"
         achieved = alg_bytes_step * args.steps / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else None
@@ -283,7 +352,8 @@ def run_b200(args):
         except Exception:
             pass
         line = {
-            "metric": METRIC, "value": round(value, 2), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if unit == "images" else "%s/sec, %s %s" % (unit, args.model, "RayShardedStrategy" if args.strategy == "sharded" else "RayStrategy"),
+            "value": round(value, 2), "unit": unit + "/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.wire == "bf16" else "fp32", "data": "synthetic",
             "config": {"workload": "%s synthetic 224x224 RayStrategy(num_workers=%d, use_gpu=True) bf16-autocast, "
@@ -291,22 +361,24 @@ def run_b200(args):
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
                        "bucket_cap_mb": args.bucket_cap_mb, "grad_elements": n_params,
                        "l2_policy": "inputs larger than L2 (activations + 97.5 MiB of gradients per step >> 126 MB)",
-                       "algo": args.algo, "mem": args.mem, "nvls_bound": bool(comm.nvls)},
-            "e2e": {"value": round(e2e_value, 2), "unit": "images/sec", "ms_per_step": round(e2e_ms / args.steps, 3),
-                    "h2d_bytes_per_step": int(host_x.numel() * 4 + host_y.numel() * 8) * world,
+                       "algo": args.algo, "mem": args.mem, "nvls_bound": bool(getattr(comm, "nvls", False)),
+                       "strategy": args.strategy, "hook": args.hook},
+            "e2e": {"value": round(e2e_value, 2), "unit": unit + "/sec", "ms_per_step": round(e2e_ms / args.steps, 3),
+                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)) * world,
                     "d2h_bytes_per_step": 4 * world,
                     "api": "RayStrategy worker path: training_step/backward/optimizer.step with pinned-host batches, loss read back"},
             "gpu_launches": launches_timed,
             "roofline": {"bound": bound, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": unit,
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
-                         "kernel": "k0_cast_scale_kernel<bf16>" if world == 1 else "k1/k2 fused allreduce",
+                         "kernel": ("k456_sharded_kernel" if args.strategy == "sharded" else
+                                    "k0_cast_scale_kernel<bf16>" if world == 1 else "k1/k2 fused allreduce") if args.hook == "b200" else None,
                          "algorithmic_bytes_per_step": alg_bytes_step, "launches_per_step": buckets_per_step,
                          "avg_launch_ms": round(per_launch_ms, 5), "kernel_share_of_step": round(kernel_ms / total_ms, 5),
                          "peak_source": peak_note,
                          "note": "launch durations from CUDA events on the comm stream inside the timed region (overlapped with backward)"},
-            "clocks": clocks, "final_loss": last_loss,
+            "clocks": clocks, "final_loss": last_loss if isinstance(last_loss, float) else float(last_loss),
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.model.startswith("resnet"):
             try:
                 cb = cpu_reference(1, args.cpu_batch, 2, 1, args.model)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
   {
     const size_t base = static_cast<size_t>(P.rank) * slice;
     if constexpr (NVLS) {
-      constexpr int U = 8;
+      constexpr int U = kMaxLoadsInFlight;
       const uint4* mc = reinterpret_cast<const uint4*>(P.peers.mc_arena + P.stage_off);
       for (size_t j = g; j < slice; j += gt * U) {
         uint4 red[U];
