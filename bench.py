@@ -322,6 +322,33 @@ def run_b200(args):
     timed_launches = int(st["timed_launches"])
     e2e_ms, last_loss = timed(args.steps, e2e=True)
 
+    # The same buckets once more, ISOLATED (no backward running, ranks aligned by a barrier): what the
+    # kernel does when it is not waiting for SMs or for a slower peer.  Through the same hook entry point.
+    isolated = None
+    if state is not None and comm is not None and getattr(state, "seen", None):
+        isolated = []
+        for idx, n in sorted(state.seen.items()):
+            buf = torch.randn(n, device=dev) * 0.01
+            barrier()
+            for _ in range(3):
+                comm.allreduce_(buf, bucket_idx=idx, wire=args.wire, algo=args.algo, wait_stream=state.stream,
+                                comm_stream=state.stream)
+            barrier()
+            it = 20
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(state.stream):
+                a.record()
+                for _ in range(it):
+                    comm.allreduce_(buf, bucket_idx=idx, wire=args.wire, algo=args.algo, wait_stream=state.stream,
+                                    comm_stream=state.stream)
+                b.record()
+            b.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / it], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            isolated.append((idx, n, float(t)))
+        barrier()
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         ms_per_step = total_ms / args.steps
@@ -335,13 +362,13 @@ def run_b200(args):
             alg_bytes_step = 8.0 * n_params
             if args.strategy == "sharded":   # stage (4 r + w w), reduce (w r), Adam p/m/v r+w + p (28), DESIGN.md §4
                 alg_bytes_step = (4.0 + 2 * wire_w + 28.0) * n_params
-            bound, peak, unit = "hbm", float(peaks["hbm_gbs"]), "GB/s"
+            bound, peak, runit = "hbm", float(peaks["hbm_gbs"]), "GB/s"
             peak_note = "MEASURED_PEAKS.json hbm_gbs (%s)" % peak_src
         else:
             alg_bytes_step = 2.0 * (world - 1) / world * n_params * wire_w   # NCCL-tests bus-bandwidth convention
             if args.strategy == "sharded":   # reduce-scatter at wire width + fp32 parameter all-gather
                 alg_bytes_step = (world - 1) / world * n_params * (wire_w + 4.0)
-            bound, peak, unit = "nvlink", NVLINK_PEAK_GBS, "GB/s"
+            bound, peak, runit = "nvlink", NVLINK_PEAK_GBS, "GB/s"
             peak_note = "fallback: B200_PROFILING.md measured peer copy 770 GB/s per direction (not in MEASURED_PEAKS.json)"
         achieved = alg_bytes_step * args.steps / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else None
         traffic = None
@@ -368,7 +395,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 4 * world,
                     "api": "RayStrategy worker path: training_step/backward/optimizer.step with pinned-host batches, loss read back"},
             "gpu_launches": launches_timed,
-            "roofline": {"bound": bound, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": unit,
+            "roofline": {"bound": bound, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": runit,
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                          "kernel": ("k456_sharded_kernel" if args.strategy == "sharded" else
                                     "k0_cast_scale_kernel<bf16>" if world == 1 else "k1/k2 fused allreduce") if args.hook == "b200" else None,
@@ -377,6 +404,14 @@ def run_b200(args):
                          "peak_source": peak_note,
                          "note": "launch durations from CUDA events on the comm stream inside the timed region (overlapped with backward)"},
             "clocks": clocks, "final_loss": last_loss if isinstance(last_loss, float) else float(last_loss),
+            "allreduce_isolated": None if not isolated else {
+                "note": "same bucket sizes, back to back on the comm stream with no backward running (L2-warm), max over ranks",
+                "buckets": [{"index": i, "elements": n, "ms": round(ms, 5),
+                             "GBps": round((8.0 * n if world == 1 else 2.0 * (world - 1) / world * n * (2 if args.wire == "bf16" else 4)) / ms / 1e6, 1)}
+                            for i, n, ms in isolated],
+                "GBps_total": round(sum((8.0 * n if world == 1 else 2.0 * (world - 1) / world * n * (2 if args.wire == "bf16" else 4))
+                                        for _, n, _ in isolated) / sum(ms for _, _, ms in isolated) / 1e6, 1),
+                "unit": "HBM GB/s (8 B/element)" if world == 1 else "NVLink bus GB/s (2(W-1)/W x wire bytes)"},
         }
         if not args.no_cpu_baseline and world == 1 and args.model.startswith("resnet"):
             try:

@@ -202,6 +202,10 @@ typedef struct b2d_stats {
 
 int b2d_ctx_stats(b2d_ctx* ctx, b2d_stats* out);   /* resolves finished timing events */
 int b2d_ctx_reset_stats(b2d_ctx* ctx);
+/* Debug: per-phase device times of the LAST allreduce launch.  enable=1 allocates the stamp buffer;
+ * phase_us (>= 8 doubles) receives the mean over blocks of each interval between consecutive stamps
+ * (two-shot: stage, barrier, reduce, barrier, gather) followed by max(end)-min(start); synchronises. */
+int b2d_ctx_trace(b2d_ctx* ctx, int enable, double* phase_us, int* n_phases);
 /* The algorithm AUTO would pick and the grid it would launch, without launching. */
 int b2d_plan(b2d_ctx* ctx, size_t n, int wire, int algo, int* algo_out, int* grid_out, int* block_out);
 

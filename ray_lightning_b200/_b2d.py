@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "b2d_mc_bind", "b2d_ctx_destroy", "b2d_last_error", "b2d_ctx_set_timeout", "b2d_ctx_set_max_ctas",
     "b2d_ctx_set_one_shot_max_bytes", "b2d_allreduce_bucket", "b2d_sharded_step", "b2d_reduce_scatter",
     "b2d_allgather", "b2d_barrier", "b2d_arena_alloc", "b2d_arena_reset", "b2d_ctx_stats",
-    "b2d_ctx_reset_stats", "b2d_plan",
+    "b2d_ctx_reset_stats", "b2d_plan", "b2d_ctx_trace",
 ]
 
 
@@ -96,6 +96,7 @@ def _declare(lib):
         "b2d_ctx_stats": [vp, c.POINTER(Stats)],
         "b2d_ctx_reset_stats": [vp],
         "b2d_plan": [vp, sz, c.c_int, c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)],
+        "b2d_ctx_trace": [vp, c.c_int, c.POINTER(c.c_double), c.POINTER(c.c_int)],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -263,6 +264,16 @@ class Context:
 
     def reset_stats(self):
         self._check(self._lib.b2d_ctx_reset_stats(self._ctx))
+
+    def trace(self, enable=True, read=False):
+        """Debug: enable phase stamping / read the last launch's per-phase microseconds."""
+        if not read:
+            self._check(self._lib.b2d_ctx_trace(self._ctx, int(enable), None, None))
+            return None
+        buf = (ctypes.c_double * 8)()
+        n = ctypes.c_int(0)
+        self._check(self._lib.b2d_ctx_trace(self._ctx, int(enable), buf, ctypes.byref(n)))
+        return [buf[i] for i in range(n.value)]
 
     def plan(self, n, wire, algo=ALGO_AUTO):
         a, g, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()

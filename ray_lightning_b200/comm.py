@@ -362,6 +362,7 @@ class B200HookState:
         self.comm = None
         self.stream = None
         self.calls = 0
+        self.seen = {}   # bucket index -> elements, as last seen (introspection for benchmarks/tests)
 
     def ensure(self, device):
         if self.comm is not None:
@@ -406,6 +407,7 @@ def b200_allreduce_hook(state: B200HookState, bucket: dist.GradBucket) -> torch.
     comm.allreduce_(buf, bucket.index(), wire=state.wire, scale=1.0 / comm.world, algo=state.algo,
                     wait_stream=cur, comm_stream=state.stream)
     state.calls += 1
+    state.seen[bucket.index()] = buf.numel()
     fut = torch.futures.Future(devices=[buf.device])
     with torch.cuda.stream(state.stream):
         fut.set_result(buf)

@@ -175,6 +175,9 @@ struct b2d_ctx {
   size_t slot_top = 0;     // slots grow up from just above the signal pad
   size_t user_bottom = 0;  // user allocations grow down from the end of the arena
 
+  unsigned long long* trace_dev = nullptr;   // debug: per-block phase stamps of the LAST allreduce launch
+  int trace_grid = 0;
+
   int max_ctas = 64;
   size_t one_shot_max_bytes = 256 * 1024;
   unsigned timeout_ms = 10000;
@@ -316,6 +319,7 @@ ArParams make_ar_params(b2d_ctx* ctx) {
   P.timeout_ns = static_cast<unsigned long long>(ctx->timeout_ms) * 1000000ull;
   P.diag = ctx->diag_dev;
   P.peers = ctx->peers;
+  P.trace = nullptr;
   return P;
 }
 
@@ -750,6 +754,7 @@ int b2d_ctx_destroy(b2d_ctx* ctx) {
     if (ctx->vmm_handle != 0) g_drv.MemRelease(ctx->vmm_handle);
     if (ctx->own_fd >= 0) close(ctx->own_fd);
     if (ctx->diag_host != nullptr) cudaFreeHost(ctx->diag_host);
+    if (ctx->trace_dev != nullptr) cudaFree(ctx->trace_dev);
     cudaGetLastError();
   }
   delete ctx;
@@ -771,6 +776,44 @@ int b2d_ctx_set_max_ctas(b2d_ctx* ctx, int max_ctas) {
 int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes) {
   if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
   ctx->one_shot_max_bytes = wire_bytes;
+  return B2D_OK;
+}
+
+int b2d_ctx_trace(b2d_ctx* ctx, int enable, double* phase_us, int* n_phases) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  if (enable && ctx->trace_dev == nullptr) {
+    void* p = nullptr;
+    B2D_CUDA(ctx, cudaMalloc(&p, sizeof(unsigned long long) * B2D_MAX_BLOCKS * kTraceSlots));
+    B2D_CUDA(ctx, cudaMemset(p, 0, sizeof(unsigned long long) * B2D_MAX_BLOCKS * kTraceSlots));
+    ctx->trace_dev = static_cast<unsigned long long*>(p);
+  }
+  if (phase_us != nullptr && n_phases != nullptr) {
+    *n_phases = 0;
+    if (ctx->trace_dev != nullptr && ctx->trace_grid > 0) {
+      B2D_CUDA(ctx, cudaDeviceSynchronize());
+      std::vector<unsigned long long> h(static_cast<size_t>(ctx->trace_grid) * kTraceSlots);
+      B2D_CUDA(ctx, cudaMemcpy(h.data(), ctx->trace_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      // phase k = mean over blocks of stamp[k+1] - stamp[k]; slot kTraceSlots-1 reports max(end) - min(start)
+      unsigned long long t0 = ~0ull, t1 = 0;
+      int used = 0;
+      for (int k = 0; k + 1 < kTraceSlots; ++k) {
+        double sum = 0; int cnt = 0;
+        for (int b = 0; b < ctx->trace_grid; ++b) {
+          const unsigned long long a = h[static_cast<size_t>(b) * kTraceSlots + k], e = h[static_cast<size_t>(b) * kTraceSlots + k + 1];
+          if (a != 0 && e != 0 && e >= a) { sum += static_cast<double>(e - a); cnt++; t0 = a < t0 ? a : t0; t1 = e > t1 ? e : t1; }
+        }
+        if (cnt == 0) break;
+        phase_us[k] = sum / cnt / 1e3;
+        used = k + 1;
+      }
+      phase_us[used] = t1 > t0 ? static_cast<double>(t1 - t0) / 1e3 : 0.0;
+      *n_phases = used + 1;
+      B2D_CUDA(ctx, cudaMemset(ctx->trace_dev, 0, sizeof(unsigned long long) * B2D_MAX_BLOCKS * kTraceSlots));
+    }
+  }
+  if (!enable && ctx->trace_dev != nullptr) { cudaFree(ctx->trace_dev); ctx->trace_dev = nullptr; }
   return B2D_OK;
 }
 
@@ -831,6 +874,8 @@ int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, in
 
   ArParams P = make_ar_params(ctx);
   P.grad = grad; P.n = n; P.stage_off = stage_off; P.scale = scale;
+  P.trace = ctx->trace_dev;
+  ctx->trace_grid = grid;
   LaunchScope ls{ctx};
   rc = ls.begin(wait_stream, comm_stream);
   if (rc != B2D_OK) return rc;

@@ -20,7 +20,10 @@ namespace b2d {
 constexpr int kThreads = 512;
 constexpr int kMaxLoadsInFlight = 16;  // 16-byte loads per thread per batch
 
+constexpr int kTraceSlots = 8;  // globaltimer stamps per block: start, after each phase / barrier
+
 struct ArParams {
+  unsigned long long* trace;  // [gridDim.x][kTraceSlots] or nullptr (debug: b2d_ctx_trace)
   float* grad;        // this rank's flat fp32 bucket (in/out)
   size_t n;           // elements
   size_t stage_off;   // byte offset of this call's staging buffer inside every arena
@@ -30,6 +33,11 @@ struct ArParams {
   Diag* diag;
   Peers peers;
 };
+
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot) {
+  if (trace != nullptr && threadIdx.x == 0)
+    trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = global_timer_ns();
+}
 
 // ---- pack helpers ------------------------------------------------------------------------
 template <int EPP>
@@ -205,6 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_one_shot_kernel(const __grid_c
   const size_t gt = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   uint4* my_stage = reinterpret_cast<uint4*>(P.peers.arena[P.rank] + P.stage_off);
+  trace_stamp(P.trace, 0);
 
   {
     constexpr int B = BF16 ? 8 : 16;  // 16 x 16-byte loads in flight per thread
@@ -216,7 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1) k1_one_shot_kernel(const __grid_c
       stage_batch<BF16, B>(P.grad, P.n, my_stage, p, ok, P.scale);
     }
   }
+  trace_stamp(P.trace, 1);
   block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
+  trace_stamp(P.trace, 2);
 
   constexpr int WW = W > 0 ? W : B2D_MAX_WORLD;
   constexpr int U = (W > 0 && kMaxLoadsInFlight / W > 1) ? kMaxLoadsInFlight / W : 1;
@@ -247,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_one_shot_kernel(const __grid_c
       }
     }
   }
+  trace_stamp(P.trace, 3);
 }
 
 // ---- K2: two-shot ------------------------------------------------------------------------
@@ -266,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
   const size_t gt = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   uint4* my_stage = reinterpret_cast<uint4*>(P.peers.arena[P.rank] + P.stage_off);
+  trace_stamp(P.trace, 0);
 
   // phase 0: stage pack j of EVERY slice (peers' thread g will read exactly these);
   // UJ consecutive j per iteration so that 16 x 16-byte loads are in flight per thread
@@ -288,7 +301,9 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
       stage_batch<BF16, B>(P.grad, P.n, my_stage, p, ok, P.scale);
     }
   }
+  trace_stamp(P.trace, 1);
   block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
+  trace_stamp(P.trace, 2);
 
   // phase 1: reduce my slice
   {
@@ -340,7 +355,9 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
       }
     }
   }
+  trace_stamp(P.trace, 3);
   block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
+  trace_stamp(P.trace, 4);
 
   // phase 2: all-gather + fp32 write-back, again 16 loads in flight per thread
   {
@@ -374,6 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
       }
     }
   }
+  trace_stamp(P.trace, 5);
 }
 
 // ---- K4/K5/K6: sharded step ----------------------------------------------------------------

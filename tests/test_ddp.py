@@ -230,3 +230,51 @@ def test_launch_without_trainer_is_rejected(ray_start_2_cpus):
 
     with pytest.raises((NotImplementedError, AttributeError)):
         launcher.launch(lambda: None, trainer=None)
+
+
+@pytest.mark.parametrize("num_gpus_per_worker,expect", [(0.4, [["0"], ["0"]]), (0.5, [["0"], ["0"]]),
+                                                         (1, [["0"], ["1"]]), (2, [["0", "1"], ["2", "3"]])])
+def test_gpu_ids_and_shared_visibility(num_gpus_per_worker, expect):
+    """GPU bin packing + CUDA_VISIBLE_DEVICES sharing (reference tests/test_ddp_gpu.py:82-123 and
+    launchers/ray_launcher.py:177-219), exercised without GPUs: ids are bookkeeping, not devices."""
+    ray.init(num_cpus=2, num_gpus=4)
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            strategy = RayStrategy(num_workers=2, use_gpu=True, resources_per_worker={"GPU": num_gpus_per_worker})
+        launcher = RayLauncher(strategy)
+        launcher.setup_workers(tune_enabled=False)
+        ids = [ray.get(w.get_node_and_gpu_ids.remote())[1] for w in launcher._workers]
+        assert ids == expect
+        union = []
+        for g in sum(expect, []):
+            if g not in union:
+                union.append(g)
+        vis = ray.get([w.execute.remote(lambda: os.environ.get("CUDA_VISIBLE_DEVICES")) for w in launcher._workers])
+        assert vis == [",".join(union)] * 2
+        assert ray.get(launcher._workers[0].execute.remote(lambda: os.environ.get("CUDA_DEVICE_ORDER"))) == "PCI_BUS_ID"
+        assert launcher.get_local_ranks() == [(0, 0), (1, 0)]
+        launcher.teardown_workers()
+    finally:
+        ray.shutdown()
+
+
+def test_root_device_is_the_position_in_the_shared_list(monkeypatch):
+    """root_device.index = index of the worker's GPU id inside CUDA_VISIBLE_DEVICES (reference ray_ddp.py:259-304)."""
+    s = RayStrategy(num_workers=2, use_gpu=True)
+    assert s.root_device == torch.device("cpu") or s.root_device == torch.device("cuda:0")   # driver side
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    assert s.root_device == torch.device("cuda:0")             # driver: any device
+    s.set_remote(True)
+    monkeypatch.setattr(ray, "get_gpu_ids", lambda: [2])
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "0,1,2,3")
+    assert s.root_device == torch.device("cuda:2")
+    monkeypatch.setattr(ray, "get_gpu_ids", lambda: ["3", "1"])  # several: the first one wins
+    assert s.root_device == torch.device("cuda:3")
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "0,1")
+    with pytest.raises(RuntimeError, match="CUDA_VISIBLE_DEVICES set incorrectly"):
+        s.root_device
+    s.root_device = torch.device("cuda:1")                      # the launcher pins it (ray_launcher.py:296)
+    assert s.root_device == torch.device("cuda:1")
+    assert s.distributed_sampler_kwargs == dict(num_replicas=2, rank=0)
