@@ -383,8 +383,10 @@ def run_b200(args):
             "value": round(value, 2), "unit": unit + "/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.wire == "bf16" else "fp32", "data": "synthetic",
-            "config": {"workload": "%s synthetic 224x224 RayStrategy(num_workers=%d, use_gpu=True) bf16-autocast, "
-                                   "DDP comm hook = libb2d fused allreduce (%s wire)" % (args.model, world, args.wire),
+            "config": {"workload": "%s synthetic %s %s(num_workers=%d, use_gpu=True) bf16-autocast, gradient sync = %s"
+                                   % (args.model, "224x224" if unit == "images" else "token ids",
+                                      "RayShardedStrategy" if args.strategy == "sharded" else "RayStrategy", world,
+                                      ("libb2d (%s wire)" % args.wire) if args.hook == "b200" else args.hook),
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
                        "bucket_cap_mb": args.bucket_cap_mb, "grad_elements": n_params,
                        "l2_policy": "inputs larger than L2 (activations + 97.5 MiB of gradients per step >> 126 MB)",

@@ -78,7 +78,9 @@ typedef enum b2d_algo {
   B2D_ALGO_AUTO = 0,
   B2D_ALGO_ONE_SHOT = 1,   /* every rank reads every peer's whole staged bucket */
   B2D_ALGO_TWO_SHOT = 2,   /* reduce-scatter of 1/W slices + all-gather, both by peer reads */
-  B2D_ALGO_NVLS = 3        /* multimem.ld_reduce / multimem.st through the NVSwitch */
+  B2D_ALGO_NVLS = 3,       /* multimem.ld_reduce / multimem.st through the NVSwitch */
+  B2D_ALGO_TWO_SHOT_TMA = 4 /* two-shot with every load a TMA bulk copy into a shared-memory ring (bf16 wire,
+                               n % 8 == 0; other shapes fall back to B2D_ALGO_TWO_SHOT) */
 } b2d_algo;
 
 /* b2d_ctx_create flags */
@@ -130,6 +132,7 @@ const char* b2d_last_error(b2d_ctx* ctx);
 
 int b2d_ctx_set_timeout(b2d_ctx* ctx, unsigned timeout_ms);  /* peer-flag watchdog; default 10000 */
 int b2d_ctx_set_max_ctas(b2d_ctx* ctx, int max_ctas);        /* CTAs per comm kernel; default 128 */
+int b2d_ctx_set_tma_ctas(b2d_ctx* ctx, int ctas);            /* CTAs of the TMA-staged kernel; default 48 */
 int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes); /* AUTO: one-shot at or below */
 
 /* ---- data path ------------------------------------------------------------------------- */

@@ -15,11 +15,12 @@ MAX_WORLD = 8
 MAX_BLOCKS = 296
 
 WIRE_FP32, WIRE_BF16 = 0, 1
-ALGO_AUTO, ALGO_ONE_SHOT, ALGO_TWO_SHOT, ALGO_NVLS = 0, 1, 2, 3
+ALGO_AUTO, ALGO_ONE_SHOT, ALGO_TWO_SHOT, ALGO_NVLS, ALGO_TWO_SHOT_TMA = 0, 1, 2, 3, 4
 FLAG_MEM_LEGACY_IPC, FLAG_MEM_VMM, FLAG_TIMING = 0x0, 0x1, 0x2
 
 WIRE_NAMES = {"fp32": WIRE_FP32, "bf16": WIRE_BF16}
-ALGO_NAMES = {"auto": ALGO_AUTO, "one_shot": ALGO_ONE_SHOT, "two_shot": ALGO_TWO_SHOT, "nvls": ALGO_NVLS}
+ALGO_NAMES = {"auto": ALGO_AUTO, "one_shot": ALGO_ONE_SHOT, "two_shot": ALGO_TWO_SHOT, "nvls": ALGO_NVLS,
+              "two_shot_tma": ALGO_TWO_SHOT_TMA}
 
 # every symbol include/b2d.h declares (checked by tests/test_cabi.py on a GPU-less box)
 EXPORTED_SYMBOLS = [
@@ -28,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "b2d_mc_bind", "b2d_ctx_destroy", "b2d_last_error", "b2d_ctx_set_timeout", "b2d_ctx_set_max_ctas",
     "b2d_ctx_set_one_shot_max_bytes", "b2d_allreduce_bucket", "b2d_sharded_step", "b2d_reduce_scatter",
     "b2d_allgather", "b2d_barrier", "b2d_arena_alloc", "b2d_arena_reset", "b2d_ctx_stats",
-    "b2d_ctx_reset_stats", "b2d_plan", "b2d_ctx_trace",
+    "b2d_ctx_reset_stats", "b2d_plan", "b2d_ctx_trace", "b2d_ctx_set_tma_ctas",
 ]
 
 
@@ -84,6 +85,7 @@ def _declare(lib):
         "b2d_ctx_destroy": [vp],
         "b2d_ctx_set_timeout": [vp, c.c_uint],
         "b2d_ctx_set_max_ctas": [vp, c.c_int],
+        "b2d_ctx_set_tma_ctas": [vp, c.c_int],
         "b2d_ctx_set_one_shot_max_bytes": [vp, sz],
         "b2d_allreduce_bucket": [vp, c.c_int, vp, sz, c.c_int, c.c_float, c.c_int, vp, vp],
         "b2d_sharded_step": [vp, c.c_int, vp, vp, vp, vp, sz, c.POINTER(c.c_int64), c.c_int, c.c_float,
@@ -217,6 +219,9 @@ class Context:
 
     def set_max_ctas(self, n):
         self._check(self._lib.b2d_ctx_set_max_ctas(self._ctx, int(n)))
+
+    def set_tma_ctas(self, n):
+        self._check(self._lib.b2d_ctx_set_tma_ctas(self._ctx, int(n)))
 
     def set_one_shot_max_bytes(self, n):
         self._check(self._lib.b2d_ctx_set_one_shot_max_bytes(self._ctx, int(n)))

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "b2d_kernels.cuh"
+#include "b2d_tma.cuh"
 
 using namespace b2d;
 
@@ -179,6 +180,8 @@ struct b2d_ctx {
   int trace_grid = 0;
 
   int max_ctas = 128;
+  int tma_ctas = 48;        // CTAs of the TMA-staged kernel (b2d_ctx_set_max_ctas caps it too)
+  int tma_ctas_user = 0;
   size_t one_shot_max_bytes = 1024 * 1024;
   unsigned timeout_ms = 10000;
   int last_algo = 0, last_grid = 0, last_block = 0;
@@ -334,6 +337,7 @@ int launch_barrier(b2d_ctx* ctx, cudaStream_t stream) {
 
 int pick_algo(b2d_ctx* ctx, size_t n, int wire, int algo) {
   if (ctx->world == 1) return B2D_ALGO_ONE_SHOT;
+  if (algo == B2D_ALGO_TWO_SHOT_TMA && (wire != B2D_WIRE_BF16 || n % 8 != 0)) return B2D_ALGO_TWO_SHOT;
   if (algo != B2D_ALGO_AUTO) return algo;
   const size_t wire_bytes = n * (wire == B2D_WIRE_BF16 ? 2 : 4);
   // at world 2 one-shot moves exactly the two-shot's bytes with one barrier less
@@ -343,9 +347,25 @@ int pick_algo(b2d_ctx* ctx, size_t n, int wire, int algo) {
   return B2D_ALGO_TWO_SHOT;
 }
 
+// macro-tile size (packs) of the TMA kernel for a given grid: spread the slice over the grid, 8..4096
+int tma_mt(size_t slice, int grid) {
+  size_t mt = (slice + grid - 1) / grid;
+  mt = (mt + 7) / 8 * 8;
+  if (mt < 8) mt = 8;
+  if (mt > static_cast<size_t>(kTmaMaxMt)) mt = kTmaMaxMt;
+  return static_cast<int>(mt);
+}
+
 int pick_grid(b2d_ctx* ctx, size_t n, int wire, int algo) {
   const size_t epp = wire == B2D_WIRE_BF16 ? 8 : 4;
   const size_t npacks = (n + epp - 1) / epp;
+  if (algo == B2D_ALGO_TWO_SHOT_TMA) {
+    const size_t slice = (npacks + ctx->world - 1) / ctx->world;
+    size_t grid = (slice + 255) / 256;   // at least 4 KiB of wire per block and slice
+    if (grid < 1) grid = 1;
+    if (grid > static_cast<size_t>(ctx->tma_ctas)) grid = ctx->tma_ctas;
+    return static_cast<int>(grid);
+  }
   size_t work = npacks;
   if (algo != B2D_ALGO_ONE_SHOT) work = (npacks + ctx->world - 1) / ctx->world;
   size_t grid = (work + kThreads - 1) / kThreads;
@@ -427,10 +447,17 @@ void preload_world() {
   preload_one(k2_two_shot_kernel<W, false, false>);
   preload_one(k2_two_shot_kernel<W, true, true>);
   preload_one(k2_two_shot_kernel<W, false, true>);
+  preload_one(k2t_two_shot_tma_kernel<W, true>);
   preload_one(k456_sharded_kernel<W, true>);
   preload_one(k456_sharded_kernel<W, false>);
 }
+template <int W>
+void tma_attr() {
+  if (cudaFuncSetAttribute(k2t_two_shot_tma_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes) != cudaSuccess)
+    cudaGetLastError();
+}
 void preload_kernels() {
+  tma_attr<0>(); tma_attr<2>(); tma_attr<4>(); tma_attr<8>();
   preload_one(k0_cast_scale_kernel<true>);
   preload_one(k0_cast_scale_kernel<false>);
   preload_one(barrier_kernel);
@@ -772,6 +799,13 @@ int b2d_ctx_set_max_ctas(b2d_ctx* ctx, int max_ctas) {
   if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
   if (max_ctas < 1 || max_ctas > B2D_MAX_BLOCKS) return fail(ctx, B2D_ERR_INVALID, "max_ctas must be in [1, %d]", B2D_MAX_BLOCKS);
   ctx->max_ctas = max_ctas;
+  ctx->tma_ctas = max_ctas < 48 ? max_ctas : (ctx->tma_ctas_user > 0 ? ctx->tma_ctas_user : 48);
+  return B2D_OK;
+}
+int b2d_ctx_set_tma_ctas(b2d_ctx* ctx, int ctas) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  if (ctas < 1 || ctas > B2D_MAX_BLOCKS) return fail(ctx, B2D_ERR_INVALID, "tma ctas must be in [1, %d]", B2D_MAX_BLOCKS);
+  ctx->tma_ctas = ctas; ctx->tma_ctas_user = ctas;
   return B2D_OK;
 }
 int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes) {
@@ -845,7 +879,7 @@ int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, in
   if (grad == nullptr && n != 0) return fail(ctx, B2D_ERR_INVALID, "grad is NULL");
   if (reinterpret_cast<uintptr_t>(grad) % 16 != 0) return fail(ctx, B2D_ERR_INVALID, "bucket buffer must be 16-byte aligned");
   if (wire != B2D_WIRE_FP32 && wire != B2D_WIRE_BF16) return fail(ctx, B2D_ERR_INVALID, "bad wire %d", wire);
-  if (algo < B2D_ALGO_AUTO || algo > B2D_ALGO_NVLS) return fail(ctx, B2D_ERR_INVALID, "bad algo %d", algo);
+  if (algo < B2D_ALGO_AUTO || algo > B2D_ALGO_TWO_SHOT_TMA) return fail(ctx, B2D_ERR_INVALID, "bad algo %d", algo);
   if (algo == B2D_ALGO_NVLS && !ctx->mc_bound && ctx->world > 1) return fail(ctx, B2D_ERR_UNSUPPORTED, "NVLS requested but no multicast object is bound");
   if (n == 0) return B2D_OK;  // empty bucket: nothing to exchange, and every rank agrees on that
   DeviceGuard guard(ctx->device);
@@ -891,6 +925,16 @@ int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, in
     case B2D_ALGO_NVLS:
       if (bf) launch_two_shot<true, true>(P, ctx->world, grid, comm); else launch_two_shot<false, true>(P, ctx->world, grid, comm);
       break;
+    case B2D_ALGO_TWO_SHOT_TMA: {
+      const int mt = tma_mt(slice, grid);
+      switch (ctx->world) {
+        case 2: k2t_two_shot_tma_kernel<2, true><<<grid, kTmaThreads, kTmaSmemBytes, comm>>>(P, mt); break;
+        case 4: k2t_two_shot_tma_kernel<4, true><<<grid, kTmaThreads, kTmaSmemBytes, comm>>>(P, mt); break;
+        case 8: k2t_two_shot_tma_kernel<8, true><<<grid, kTmaThreads, kTmaSmemBytes, comm>>>(P, mt); break;
+        default: k2t_two_shot_tma_kernel<0, true><<<grid, kTmaThreads, kTmaSmemBytes, comm>>>(P, mt); break;
+      }
+      break;
+    }
     default:
       return fail(ctx, B2D_ERR_INVALID, "bad algo %d", a);
   }

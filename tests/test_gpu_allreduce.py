@@ -101,6 +101,41 @@ def test_allreduce_bit_exact_vs_oracle(world, wire, algo):
             assert same_bits(bufs[r], want), (world, wire, algo, n, r)
 
 
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_tma_staged_two_shot_bit_exact_vs_oracle(world):
+    """K2T (cp.async.bulk into a shared-memory ring): same bits as the load/store kernels and the oracle.
+    Sizes cover one partial macro tile, ragged last tiles, many tiles per block, and the fall-back shapes."""
+    g = group(world)
+    for k, n in enumerate([8, 64, 4096, 65536 + 8, (1 << 20) + 8, 7874560, 1000, 4099]):
+        per_rank = rank_inputs(world, n, seed=20 + k)
+        want = oracle(per_rank, "bf16")
+        bufs = run(world, per_rank, "bf16", "two_shot_tma", 5000 + k)
+        for r in range(world):
+            assert same_bits(bufs[r], want), (world, n, r)
+        algo_used = g.ranks[0].ctx.stats()["last_algo"]
+        assert algo_used == (4 if n % 8 == 0 else 2)
+    # fp32 wire falls back to the load/store two-shot
+    per_rank = rank_inputs(world, 4096, seed=99)
+    bufs = run(world, per_rank, "fp32", "two_shot_tma", 5100)
+    assert same_bits(bufs[0], oracle(per_rank, "fp32"))
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_tma_back_to_back_steps(world):
+    g = group(world)
+    n = 200000
+    steps = [rank_inputs(world, n, seed=70 + s) for s in range(5)]
+    bufs = [[t.cuda() for t in per_rank] for per_rank in steps]
+    torch.cuda.synchronize()
+    for s in range(5):
+        g.allreduce_(bufs[s], bucket_idx=5200 + world, wire="bf16", algo="two_shot_tma")
+    g.synchronize()
+    for s in range(5):
+        want = oracle(steps[s], "bf16")
+        for r in range(world):
+            assert same_bits(bufs[s][r], want), (s, r)
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_auto_picks_one_shot_then_two_shot(world):
     from ray_lightning_b200 import _b2d

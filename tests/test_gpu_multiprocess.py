@@ -63,3 +63,70 @@ def test_worker_processes_share_arenas(world, mem):
         assert ret[r]["ok"], (r, dict(ret[r]))
         assert ret[r]["launches"] == 12
         assert ret[r]["mem_kind"] == (1 if mem == "vmm" else 0)
+
+
+def _ddp_worker(rank, world, port, ret):
+    """torch DDP with the libb2d hook vs (a) stock DDP, (b) the oracle on the local gradients — several
+    iterations, several buckets, including the bucket re-layout after iteration 1."""
+    import torch.distributed as dist
+    import torch.nn as nn
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from oracle import ddp_oracle
+    from ray_lightning_b200.comm import B200HookState, b200_allreduce_hook
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="env://")
+    dev = torch.device("cuda", rank % torch.cuda.device_count())
+    torch.cuda.set_device(dev)
+
+    def make():
+        torch.manual_seed(0)
+        return nn.Sequential(nn.Linear(37, 531), nn.ReLU(), nn.Linear(531, 257), nn.ReLU(), nn.Linear(257, 11)).to(dev)
+
+    def batch(it):
+        g = torch.Generator().manual_seed(100 * it + rank)
+        return torch.randn(8, 37, generator=g).to(dev), torch.randint(0, 11, (8,), generator=g).to(dev)
+
+    ok, info = True, {}
+    states = []
+    try:
+        for wire in ("fp32", "bf16"):
+            kw = dict(device_ids=[dev.index], bucket_cap_mb=0.25, find_unused_parameters=False)
+            ours, stock, plain = DDP(make(), **kw), DDP(make(), **kw), make()
+            st = B200HookState(wire=wire, total_grad_elems=sum(p.numel() for p in plain.parameters()), mem="ipc",
+                               max_ctas=32)
+            states.append(st)
+            ours.register_comm_hook(st, b200_allreduce_hook)
+            for it in range(4):
+                x, y = batch(it)
+                for m in (ours, stock, plain):
+                    m.zero_grad(set_to_none=True)
+                    nn.functional.cross_entropy(m(x), y).backward()
+                torch.cuda.synchronize()
+                local = [p.grad.detach().cpu().clone() for p in plain.parameters()]
+                gathered = [None] * world
+                dist.all_gather_object(gathered, local)
+                for i, (po, ps) in enumerate(zip(ours.parameters(), stock.parameters())):
+                    per_rank = [gathered[r][i].reshape(-1) for r in range(world)]
+                    if wire == "fp32":
+                        # world 2: one fp32 add per element -> identical to stock DDP (gloo) bit for bit
+                        ok = ok and torch.equal(po.grad, ps.grad)
+                        want = ddp_oracle.allreduce_fp32_wire(per_rank)
+                    else:
+                        want = ddp_oracle.allreduce_bf16_wire(per_rank)
+                    ok = ok and torch.equal(po.grad.cpu().reshape(-1).view(torch.int32), want.view(torch.int32))
+            info[wire] = {"calls": st.calls, "buckets_seen": len(st.seen)}
+        ret[rank] = {"ok": bool(ok), **info}
+    finally:
+        for st in states:
+            st.close()
+        dist.destroy_process_group()
+
+
+def test_ddp_with_the_hook_matches_stock_ddp_and_the_oracle():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ddp_worker, args=(2, _port(), ret), nprocs=2, join=True)
+    for r in range(2):
+        assert ret[r]["ok"], dict(ret[r])
+        assert ret[r]["fp32"]["calls"] >= 4 and ret[r]["fp32"]["buckets_seen"] >= 2   # several buckets after the re-layout

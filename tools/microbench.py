@@ -85,8 +85,10 @@ def sweep():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mem = os.environ.get("B2D_MEM", "vmm")
-    max_ctas = int(os.environ.get("B2D_MAX_CTAS", "64"))
+    max_ctas = int(os.environ.get("B2D_MAX_CTAS", "128"))
     comm = Communicator(rank, world, local, 3 << 30, mem=mem, max_ctas=max_ctas, timeout_ms=20000, nvls="auto")
+    if os.environ.get("B2D_TMA_CTAS"):
+        comm.ctx.set_tma_ctas(int(os.environ["B2D_TMA_CTAS"]))
     if rank == 0:
         print(json.dumps({"bench": "sweep_setup", "world": world, "mem": mem, "nvls": comm.nvls, "max_ctas": max_ctas}), flush=True)
     side = torch.cuda.Stream()
@@ -114,7 +116,7 @@ def sweep():
         ref = buf.clone()
         bus = 2 * (world - 1) / world * wire_bytes
         rows = {}
-        algos = ["one_shot", "two_shot"] + (["nvls"] if comm.nvls else [])
+        algos = ["one_shot", "two_shot", "two_shot_tma"] + (["nvls"] if comm.nvls and os.environ.get("B2D_SKIP_NVLS") != "1" else [])
         for algo in algos:
             if algo == "one_shot" and wire_bytes > (16 << 20):
                 continue
