@@ -35,10 +35,11 @@ def _worker(rank, world, port, mem, ret):
             per_rank = [torch.randn(n, generator=torch.Generator().manual_seed(77 + r + 10 * k)) * 0.05
                         for r in range(world)]
             for wire in ("bf16", "fp32"):
-                for algo in ("one_shot", "two_shot"):
+                for ai, algo in enumerate(("one_shot", "two_shot", "two_shot_tma")):
+                    if algo == "two_shot_tma" and wire == "fp32":
+                        continue
                     buf = per_rank[rank].cuda()
-                    comm.allreduce_(buf, bucket_idx=k * 10 + (wire == "bf16") * 2 + (algo == "one_shot"),
-                                    wire=wire, algo=algo)
+                    comm.allreduce_(buf, bucket_idx=k * 10 + (wire == "bf16") * 3 + ai, wire=wire, algo=algo)
                     torch.cuda.synchronize()
                     fn = ddp_oracle.allreduce_bf16_wire if wire == "bf16" else ddp_oracle.allreduce_fp32_wire
                     want = fn(per_rank)
@@ -61,7 +62,7 @@ def test_worker_processes_share_arenas(world, mem):
     assert sorted(ret.keys()) == list(range(world))
     for r in range(world):
         assert ret[r]["ok"], (r, dict(ret[r]))
-        assert ret[r]["launches"] == 12
+        assert ret[r]["launches"] == 15
         assert ret[r]["mem_kind"] == (1 if mem == "vmm" else 0)
 
 

@@ -138,9 +138,10 @@ def sweep():
             c = buf.to(torch.bfloat16).div_(world)
             dist.all_reduce(c)
             buf.copy_(c)
-        rows["nccl_bf16_hook_seq"] = timed(nccl_bf16, iters)
-        cb = buf.to(torch.bfloat16)
-        rows["nccl_bf16_allreduce_only"] = timed(lambda: dist.all_reduce(cb), iters)
+        if os.environ.get("B2D_SKIP_NCCL") != "1":
+            rows["nccl_bf16_hook_seq"] = timed(nccl_bf16, iters)
+            cb = buf.to(torch.bfloat16)
+            rows["nccl_bf16_allreduce_only"] = timed(lambda: dist.all_reduce(cb), iters)
         if os.environ.get("B2D_SKIP_FP32") != "1":
             rows["nccl_fp32_allreduce"] = timed(lambda: dist.all_reduce(buf), iters)
         buf.copy_(ref)
