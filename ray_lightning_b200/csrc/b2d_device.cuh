@@ -178,4 +178,47 @@ __device__ __forceinline__ void block_barrier(const Peers& peers, int rank, int 
   if (threadIdx.x == 0) self->ctr[b] = val;
 }
 
+// ---- split barrier: arrive now, consume the peers' arrivals one by one -------------------------
+// barrier_arrive() publishes this block's epoch to every peer (after making the block's writes
+// visible); poll_arrived() — called by ONE thread — returns the set of not-yet-consumed peers whose
+// same-index block has arrived, spinning until there is at least one.  Lets the all-gather start
+// with whoever is ready instead of waiting for the slowest rank (the wait at the second barrier was
+// the largest single item of the 8-GPU trace, profiles/r01_v3_sweep_8_tma32.jsonl).
+__device__ __forceinline__ uint32_t barrier_arrive(const Peers& peers, int rank, int world) {
+  __syncthreads();
+  const int b = blockIdx.x;
+  const uint32_t val = peers.signal[rank]->ctr[b] + 1u;
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_flag(&peers.signal[threadIdx.x]->flag[val & 1u][b][rank], val);
+  }
+  return val;
+}
+
+__device__ __forceinline__ uint32_t poll_arrived(const Peers& peers, int rank, int world, uint32_t val,
+                                                 uint32_t done_mask, unsigned long long timeout_ns, Diag* diag) {
+  const int b = blockIdx.x;
+  const uint32_t* mine = &peers.signal[rank]->flag[val & 1u][b][0];
+  uint32_t mask = 0;
+  const unsigned long long t0 = global_timer_ns();
+  unsigned spins = 0;
+  for (;;) {
+    for (int s = 0; s < world; ++s)
+      if (!((done_mask >> s) & 1u) && (s == rank || static_cast<int32_t>(ld_flag(mine + s) - val) >= 0)) mask |= 1u << s;
+    if (mask != 0) break;
+    if ((++spins & 0xffu) == 0 && timeout_ns != 0 && global_timer_ns() - t0 > timeout_ns) {
+      if (diag != nullptr) {
+        int first = 0;
+        while (first < world && ((done_mask >> first) & 1u)) ++first;
+        diag->rank = rank; diag->block = b; diag->peer = first; diag->expect = val; diag->got = ld_flag(mine + first);
+        diag->code = 1;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+  __threadfence_system();  // acquire
+  return mask;
+}
+
 }  // namespace b2d

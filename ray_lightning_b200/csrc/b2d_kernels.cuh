@@ -356,25 +356,22 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
     }
   }
   trace_stamp(P.trace, 3);
-  block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
-  trace_stamp(P.trace, 4);
-
-  // phase 2: all-gather + fp32 write-back, again 16 loads in flight per thread
-  {
-    constexpr int UJ = (W > 0 && kMaxLoadsInFlight / W > 1) ? kMaxLoadsInFlight / W : 1;
-    constexpr int B = WW * UJ;
-    for (size_t j = g; j < slice; j += gt * UJ) {
-      uint4 in[B];
-      size_t p[B];
-      bool ok[B];
+  constexpr int UJ2 = (W > 0 && kMaxLoadsInFlight / W > 1) ? kMaxLoadsInFlight / W : 1;
+  constexpr int B2 = WW * UJ2;
+  // one gather pass over this block's packs of the slices in `mask` (16 loads in flight per thread)
+  auto gather = [&](uint32_t mask) {
+    for (size_t j = g; j < slice; j += gt * UJ2) {
+      uint4 in[B2];
+      size_t p[B2];
+      bool ok[B2];
 #pragma unroll
-      for (int u = 0; u < UJ; ++u) {
+      for (int u = 0; u < UJ2; ++u) {
 #pragma unroll
         for (int s = 0; s < WW; ++s) {
           const int i = u * WW + s;
           const size_t jj = j + u * gt;
           p[i] = static_cast<size_t>(s) * slice + jj;
-          ok[i] = s < world && jj < slice && p[i] < npacks;
+          ok[i] = s < world && ((mask >> s) & 1u) && jj < slice && p[i] < npacks;
           if (ok[i]) {
             const unsigned char* src = NVLS ? P.peers.arena[P.rank] : P.peers.arena[s];
             in[i] = ld_peer_v4(reinterpret_cast<const uint4*>(src + P.stage_off) + p[i]);
@@ -382,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
         }
       }
 #pragma unroll
-      for (int i = 0; i < B; ++i) {
+      for (int i = 0; i < B2; ++i) {
         if (ok[i]) {
           uint4 raw[EPP / 4];
           from_wire<BF16>(in[i], raw);
@@ -390,6 +387,29 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
         }
       }
     }
+  };
+  if constexpr (NVLS) {
+    // the multicast stores of every rank land in the local arena: one barrier, one local pass
+    block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
+    trace_stamp(P.trace, 4);
+    gather(world >= 32 ? 0xffffffffu : ((1u << world) - 1u));
+  } else {
+    // phase 2: all-gather + fp32 write-back in ARRIVAL order: start with the own slice and whichever
+    // peers have finished their reduce, instead of idling until the slowest rank has
+    __shared__ uint32_t s_mask[2];
+    const uint32_t all = (1u << world) - 1u;
+    const uint32_t val = barrier_arrive(P.peers, P.rank, world);
+    trace_stamp(P.trace, 4);
+    uint32_t done = 0;
+    for (int round = 0; done != all; ++round) {
+      if (threadIdx.x == 0) s_mask[round & 1] = poll_arrived(P.peers, P.rank, world, val, done, P.timeout_ns, P.diag);
+      __syncthreads();
+      const uint32_t mask = s_mask[round & 1];
+      gather(mask);
+      done |= mask;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) P.peers.signal[P.rank]->ctr[blockIdx.x] = val;
   }
   trace_stamp(P.trace, 5);
 }
