@@ -579,27 +579,50 @@ __global__ void __launch_bounds__(kThreads, 1) k456_sharded_kernel(const __grid_
   }
 
   if (P.do_gather) {
-    block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
-    // phase 2: pull every other owner's updated fp32 parameters (4 elements per 16 B)
-    constexpr int B = (W > 0) ? (W > 8 ? 8 : W) : 4;
-    const size_t max_v4 = max_len / 4;
-    for (size_t j = g; j < max_v4; j += gt) {
-      for (int s0 = 0; s0 < world; s0 += B) {
-        uint4 in[B];
-        bool ok[B];
+    // phase 2: pull every other owner's updated fp32 parameters, in ARRIVAL order (see k2_two_shot_kernel):
+    // owners that have finished their Adam are gathered first instead of waiting for the slowest.
+    // The unit is the SAME pack (EPP elements) with the same (block, thread) -> pack mapping as in the
+    // Adam phase: owner s's per-block flag only vouches for what owner s's block b wrote.
+    constexpr int Q = EPP / 4;                               // 16-byte fp32 loads per pack
+    constexpr int B = (W > 0) ? (W * Q > 16 ? 16 / Q : W) : 4;
+    const size_t max_packs = max_len / EPP;
+    __shared__ uint32_t s_gmask[2];
+    const uint32_t all = (1u << world) - 1u;
+    const uint32_t val = barrier_arrive(P.peers, P.rank, world);
+    uint32_t done = 1u << P.rank;                            // the own shard is already in place
+    for (int round = 0; done != all; ++round) {
+      if (threadIdx.x == 0) s_gmask[round & 1] = poll_arrived(P.peers, P.rank, world, val, done, P.timeout_ns, P.diag);
+      __syncthreads();
+      const uint32_t mask = s_gmask[round & 1];
+      for (size_t j = g; j < max_packs; j += gt) {
+        for (int s0 = 0; s0 < world; s0 += B) {
+          uint4 in[B][Q];
+          bool ok[B];
 #pragma unroll
-        for (int i = 0; i < B; ++i) {
-          const int s = s0 + i;
-          ok[i] = s < world && s != P.rank && j < static_cast<size_t>(P.off[s + 1] - P.off[s]) / 4;
-          if (ok[i])
-            in[i] = ld_peer_v4(reinterpret_cast<const float*>(P.peers.arena[s] + P.param_off) +
-                               static_cast<size_t>(P.off[s]) + 4 * j);
+          for (int i = 0; i < B; ++i) {
+            const int s = s0 + i;
+            ok[i] = s < world && ((mask >> s) & 1u) && j < static_cast<size_t>(P.off[s + 1] - P.off[s]) / EPP;
+            if (ok[i]) {
+#pragma unroll
+              for (int q = 0; q < Q; ++q)
+                in[i][q] = ld_peer_v4(reinterpret_cast<const float*>(P.peers.arena[s] + P.param_off) +
+                                      static_cast<size_t>(P.off[s]) + j * EPP + 4 * q);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < B; ++i) {
+            if (ok[i]) {
+#pragma unroll
+              for (int q = 0; q < Q; ++q)
+                st_v4(P.params + static_cast<size_t>(P.off[s0 + i]) + j * EPP + 4 * q, in[i][q]);
+            }
+          }
         }
-#pragma unroll
-        for (int i = 0; i < B; ++i)
-          if (ok[i]) st_v4(P.params + static_cast<size_t>(P.off[s0 + i]) + 4 * j, in[i]);
       }
+      done |= mask;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) P.peers.signal[P.rank]->ctr[blockIdx.x] = val;
     if (P.end_barrier) block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
   }
 }
