@@ -229,3 +229,24 @@ def test_full_size_resnet50_bucket_properties(world):
     assert bool((bufs3[world - 1] == 0.5).all())
     # (4) a checksum of checksums: sum of the output equals the oracle's, bit for bit in fp64
     assert float(bufs[0].double().sum()) == float(want.double().sum())
+
+
+@pytest.mark.parametrize("world", [4, 8])
+@pytest.mark.parametrize("algo", ["one_shot", "two_shot", "two_shot_tma"])
+def test_allreduce_with_skewed_ranks(world, algo):
+    """A rotating straggler (about 1 ms of device sleep before its kernel) over 8 back-to-back steps on the
+    same slot: barriers, arrival-order gather and double buffering under skew."""
+    g = group(world)
+    n = 120008
+    steps = [rank_inputs(world, n, seed=200 + s) for s in range(8)]
+    bufs = [[t.cuda() for t in per_rank] for per_rank in steps]
+    torch.cuda.synchronize()
+    for s in range(8):
+        with torch.cuda.stream(g.ranks[(3 * s) % world].stream):
+            torch.cuda._sleep(2_000_000)
+        g.allreduce_(bufs[s], bucket_idx=9950 + ["one_shot", "two_shot", "two_shot_tma"].index(algo), wire="bf16", algo=algo)
+    g.synchronize()
+    for s in range(8):
+        want = oracle(steps[s], "bf16")
+        for r in range(world):
+            assert same_bits(bufs[s][r], want), (s, r)

@@ -118,3 +118,45 @@ def test_sharded_step_matches_adam_on_averaged_grads(world, wire, wd, adamw):
         sl = slice(shard_off[r], shard_off[r + 1])
         torch.testing.assert_close(ms[r].cpu(), st["exp_avg"][sl], rtol=1e-5, atol=1e-7)
         torch.testing.assert_close(vs[r].cpu(), st["exp_avg_sq"][sl], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("world", [4, 8])
+@pytest.mark.parametrize("wire", ["fp32", "bf16"])
+def test_sharded_step_with_skewed_ranks(world, wire):
+    """One rank at a time is held back by ~1 ms of device sleep before its kernel: every cross-rank
+    ordering assumption (stage -> reduce, Adam -> gather, step k gather -> step k+1 Adam) is exercised with
+    a straggler.  All ranks must still end every step with identical parameters equal to the reference."""
+    g = group(world)
+    _, _, _, shard_off, total = layout(world, 7)
+    p0 = torch.randn(total, generator=torch.Generator().manual_seed(21))
+    params, ms, vs = [], [], []
+    for r, rk in enumerate(g.ranks):
+        p = rk.arena_tensor(total)
+        p.copy_(p0.cuda())
+        params.append(p)
+        n_own = shard_off[r + 1] - shard_off[r]
+        ms.append(torch.zeros(max(n_own, 8), device="cuda"))
+        vs.append(torch.zeros(max(n_own, 8), device="cuda"))
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-2)
+    scale = float(np.float32(1.0) / np.float32(world))
+    steps = 8
+    all_grads = [[torch.randn(total, generator=torch.Generator().manual_seed(1000 * s + r)) * 0.1 for r in range(world)]
+                 for s in range(steps)]
+    dev_grads = [[t.cuda() for t in per_rank] for per_rank in all_grads]
+    torch.cuda.synchronize()
+    for s in range(steps):                       # launched back to back, no host sync in between
+        with torch.cuda.stream(g.ranks[s % world].stream):
+            torch.cuda._sleep(2_000_000)
+        g.sharded_step_(dev_grads[s], params, ms, vs, shard_off, step=s + 1, lr=1e-2, wire=wire, slot=40 + (wire == "bf16"))
+    g.synchronize()
+    for s in range(steps):
+        if wire == "fp32":
+            avg = ddp_oracle.allreduce_fp32_wire(all_grads[s], scale)
+        else:
+            avg = sum(ddp_oracle.wire_bf16(t, scale) for t in all_grads[s])
+        ref_p.grad = avg.clone()
+        opt.step()
+    for r in range(1, world):
+        assert torch.equal(params[r], params[0]), r
+    torch.testing.assert_close(params[0].cpu(), ref_p.detach(), rtol=1e-4, atol=1e-5)
