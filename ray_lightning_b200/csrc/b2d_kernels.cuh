@@ -388,29 +388,12 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
       }
     }
   };
-  if constexpr (NVLS) {
-    // the multicast stores of every rank land in the local arena: one barrier, one local pass
-    block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
-    trace_stamp(P.trace, 4);
-    gather(world >= 32 ? 0xffffffffu : ((1u << world) - 1u));
-  } else {
-    // phase 2: all-gather + fp32 write-back in ARRIVAL order: start with the own slice and whichever
-    // peers have finished their reduce, instead of idling until the slowest rank has
-    __shared__ uint32_t s_mask[2];
-    const uint32_t all = (1u << world) - 1u;
-    const uint32_t val = barrier_arrive(P.peers, P.rank, world);
-    trace_stamp(P.trace, 4);
-    uint32_t done = 0;
-    for (int round = 0; done != all; ++round) {
-      if (threadIdx.x == 0) s_mask[round & 1] = poll_arrived(P.peers, P.rank, world, val, done, P.timeout_ns, P.diag);
-      __syncthreads();
-      const uint32_t mask = s_mask[round & 1];
-      gather(mask);
-      done |= mask;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) P.peers.signal[P.rank]->ctr[blockIdx.x] = val;
-  }
+  // phase 2: all-gather + fp32 write-back after ONE barrier.  (An arrival-order variant — gather whichever
+  // peers have finished first, barrier_arrive/poll_arrived in b2d_device.cuh — was measured on 8 GPUs and
+  // lost: every extra round pays a full NVLink round trip; profiles/r01_v4_sweep_8_arrival_order.jsonl.)
+  block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
+  trace_stamp(P.trace, 4);
+  gather(world >= 32 ? 0xffffffffu : ((1u << world) - 1u));
   trace_stamp(P.trace, 5);
 }
 
@@ -579,21 +562,15 @@ __global__ void __launch_bounds__(kThreads, 1) k456_sharded_kernel(const __grid_
   }
 
   if (P.do_gather) {
-    // phase 2: pull every other owner's updated fp32 parameters, in ARRIVAL order (see k2_two_shot_kernel):
-    // owners that have finished their Adam are gathered first instead of waiting for the slowest.
+    // phase 2: pull every other owner's updated fp32 parameters.
     // The unit is the SAME pack (EPP elements) with the same (block, thread) -> pack mapping as in the
     // Adam phase: owner s's per-block flag only vouches for what owner s's block b wrote.
     constexpr int Q = EPP / 4;                               // 16-byte fp32 loads per pack
     constexpr int B = (W > 0) ? (W * Q > 16 ? 16 / Q : W) : 4;
     const size_t max_packs = max_len / EPP;
-    __shared__ uint32_t s_gmask[2];
-    const uint32_t all = (1u << world) - 1u;
-    const uint32_t val = barrier_arrive(P.peers, P.rank, world);
-    uint32_t done = 1u << P.rank;                            // the own shard is already in place
-    for (int round = 0; done != all; ++round) {
-      if (threadIdx.x == 0) s_gmask[round & 1] = poll_arrived(P.peers, P.rank, world, val, done, P.timeout_ns, P.diag);
-      __syncthreads();
-      const uint32_t mask = s_gmask[round & 1];
+    block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
+    const uint32_t mask = ((1u << world) - 1u) & ~(1u << P.rank);   // the own shard is already in place
+    {
       for (size_t j = g; j < max_packs; j += gt) {
         for (int s0 = 0; s0 < world; s0 += B) {
           uint4 in[B][Q];
@@ -619,10 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) k456_sharded_kernel(const __grid_
           }
         }
       }
-      done |= mask;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) P.peers.signal[P.rank]->ctr[blockIdx.x] = val;
     if (P.end_barrier) block_barrier(P.peers, P.rank, world, P.timeout_ns, P.diag);
   }
 }
