@@ -131,7 +131,7 @@ const char* b2d_last_error(b2d_ctx* ctx);
 /* ---- knobs ----------------------------------------------------------------------------- */
 
 int b2d_ctx_set_timeout(b2d_ctx* ctx, unsigned timeout_ms);  /* peer-flag watchdog; default 10000 */
-int b2d_ctx_set_max_ctas(b2d_ctx* ctx, int max_ctas);        /* CTAs per comm kernel; default 128 */
+int b2d_ctx_set_max_ctas(b2d_ctx* ctx, int max_ctas);        /* CTAs per comm kernel; default 64 */
 int b2d_ctx_set_tma_ctas(b2d_ctx* ctx, int ctas);            /* CTAs of the TMA-staged kernel; default 48 */
 int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes); /* AUTO: one-shot at or below */
 

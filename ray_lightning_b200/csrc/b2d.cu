@@ -179,7 +179,10 @@ struct b2d_ctx {
   unsigned long long* trace_dev = nullptr;   // debug: per-block phase stamps of the LAST allreduce launch
   int trace_grid = 0;
 
-  int max_ctas = 128;
+  // 64 CTAs: measured inside a ResNet-50 step on 8 GPUs a 128-CTA grid waits longer for SMs to drain from
+  // the backward kernels than it gains (avg launch 191 us vs 110 us), although it is faster in isolation
+  // (profiles/r01_final_bench_n8_cta128.json vs r01_v2_bench_n8.json).  b2d_ctx_set_max_ctas raises it.
+  int max_ctas = 64;
   int tma_ctas = 48;        // CTAs of the TMA-staged kernel (b2d_ctx_set_max_ctas caps it too)
   int tma_ctas_user = 0;
   size_t one_shot_max_bytes = 1024 * 1024;
