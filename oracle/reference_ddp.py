@@ -25,6 +25,16 @@ from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
 from torch.nn.parallel import DistributedDataParallel as DDP
 
 
+def _init_gloo(rank, world, port):
+    """The reference's rendezvous is env:// (ray_ddp.py:192-196); here the same TCPStore rendezvous is addressed
+    explicitly so that it also works when this runner is itself started under torchrun (whose
+    TORCHELASTIC_USE_AGENT_STORE would make env:// look for the launcher's store instead of ours)."""
+    for k in list(os.environ):
+        if k.startswith("TORCHELASTIC_"):
+            os.environ.pop(k)
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="tcp://127.0.0.1:%d" % port)
+
+
 def free_port():
     with closing(socket.socket(socket.AF_INET, socket.SOCK_STREAM)) as s:
         s.bind(("127.0.0.1", 0))
@@ -102,7 +112,7 @@ def _grad_sync_worker(rank, world, port, cfg, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
-    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="env://")
+    _init_gloo(rank, world, port)
     try:
         name = cfg["model"]
         torch.manual_seed(cfg.get("seed", 0))
@@ -172,7 +182,7 @@ def _train_worker(rank, world, port, cfg, ret):
     os.environ["MASTER_PORT"] = str(port)
     threads = max(1, cfg.get("threads_total", os.cpu_count() or 1) // world)
     torch.set_num_threads(threads)
-    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="env://")
+    _init_gloo(rank, world, port)
     try:
         name = cfg["model"]
         torch.manual_seed(0)
@@ -185,6 +195,9 @@ def _train_worker(rank, world, port, cfg, ret):
         batch = cfg.get("batch", 8)
         x, y = make_batch(name, batch, 1000 + rank)
         times = []
+        budget = float(cfg.get("time_budget_s", 1e9))
+        t_start = time.perf_counter()
+        stop = torch.zeros(1)
         for step in range(cfg.get("warmup", 1) + cfg.get("steps", 2)):
             dist.barrier()
             t0 = time.perf_counter()
@@ -192,10 +205,16 @@ def _train_worker(rank, world, port, cfg, ret):
             loss = loss_fn(name, ddp(x), y)
             loss.backward()
             opt.step()
-            float(loss)
+            float(loss.detach())
             dist.barrier()
             if step >= cfg.get("warmup", 1):
                 times.append(time.perf_counter() - t0)
+            # bounded sample: rank 0 ends the run once the wall-clock budget is spent (>= 1 timed step)
+            if rank == 0 and times and time.perf_counter() - t_start > budget:
+                stop.fill_(1)
+            dist.broadcast(stop, src=0)
+            if stop.item() > 0:
+                break
         if rank == 0:
             ret["times"] = times
             ret["threads_per_rank"] = threads
@@ -215,7 +234,7 @@ def _allreduce_worker(rank, world, port, cfg, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
-    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="env://")
+    _init_gloo(rank, world, port)
     try:
         res = {}
         for nbytes in cfg["sizes"]:
