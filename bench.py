@@ -28,7 +28,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "images/sec, ResNet-50 RayStrategy (+ allreduce bus GB/s)"
-N_PARAMS_RESNET50 = 25557032
 NVLINK_PEAK_GBS = 770.0   # /opt/skills/guides/B200_PROFILING.md: measured peer copy per direction (fallback: not in MEASURED_PEAKS.json)
 
 

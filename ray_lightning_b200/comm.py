@@ -22,8 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import _b2d
-from ._b2d import (ALGO_AUTO, ALGO_NAMES, ALGO_NVLS, ALGO_ONE_SHOT, ALGO_TWO_SHOT, FLAG_MEM_VMM,
-                   FLAG_TIMING, WIRE_BF16, WIRE_FP32, WIRE_NAMES, AdamParams, B2DError)
+from ._b2d import ALGO_NAMES, FLAG_MEM_VMM, FLAG_TIMING, WIRE_NAMES, AdamParams, B2DError
 
 __all__ = ["Communicator", "LoopbackGroup", "B200HookState", "b200_allreduce_hook", "arena_bytes_for",
            "arena_tensor"]

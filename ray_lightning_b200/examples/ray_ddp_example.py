@@ -9,7 +9,6 @@ ref :24-28.
     python -m ray_lightning_b200.examples.ray_ddp_example --num-workers 2 --use-gpu  # libb2d hook
 """
 import argparse
-import os
 import tempfile
 
 import torch
