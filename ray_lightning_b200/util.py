@@ -1,62 +1,63 @@
-"""Driver-side helpers of the launcher: result pump, state-dict byte stream, device binding.
-Mirrors ray_lightning/util.py:42-102 (control plane; no gradient bytes pass here)."""
+"""Driver-side helpers of the launcher — control plane only, no gradient bytes pass here.
+
+Counterparts of ray_lightning/util.py:42-102 with the same names:
+  process_results      poll the worker futures while running the closures they queue (ref :57-70)
+  to_state_stream /    the rank-0 -> driver wire format of the trained weights: ``torch.save`` bytes
+  load_state_stream    (ref :73-92; a temp file would not survive a multi-node run)
+  set_cuda_device_if_used   late device binding in the worker (ref :95-102)
+  Unavailable          placeholder for optional integrations that are not installed (ref :42-46)
+"""
 import io
-from typing import Callable
 
 import torch
 
-from ._compat import ray, rank_zero_info
+from ._compat import rank_zero_info, ray
 
 
 class Unavailable:
-    """No object should be instance of this class (ray_lightning/util.py:42-46)."""
+    """Stands in for a class of a missing optional dependency; cannot be instantiated."""
 
-    def __init__(self, *args, **kwargs):
+    def __init__(self, *_args, **_kwargs):
         raise RuntimeError("This class should never be instantiated.")
 
 
-def _handle_queue(queue):
-    """Run the closures workers have queued for the driver (ray_lightning/util.py:49-54)."""
+def _handle_queue(queue) -> None:
+    """Execute every closure currently queued by the workers (items are ``(rank, callable)``)."""
     while not queue.empty():
-        (actor_rank, item) = queue.get()
-        if isinstance(item, Callable):
+        _rank, item = queue.get()
+        if callable(item):
             item()
 
 
 def process_results(training_result_futures, queue=None):
-    """Drain the queue while the worker futures are outstanding, then return their results
-    (ray_lightning/util.py:57-70).  A failed worker surfaces here as the exception of ray.get."""
-    not_ready = training_result_futures
-    ready = []
-    while not_ready:
+    """Block until every worker future is done, draining ``queue`` meanwhile; a failed worker raises
+    here (through ``ray.get``).  Returns the list of worker results."""
+    pending = list(training_result_futures)
+    while pending:
         if queue:
             _handle_queue(queue)
-        ready, not_ready = ray.wait(not_ready, timeout=0)
-        ray.get(ready)
-    ray.get(ready)
+        finished, pending = ray.wait(pending, timeout=0)
+        ray.get(finished)            # surfaces a worker exception as soon as it exists
     if queue:
-        _handle_queue(queue)
-    return ray.get(training_result_futures)
+        _handle_queue(queue)         # whatever was queued right before the last worker returned
+    return ray.get(list(training_result_futures))
 
 
-def to_state_stream(model_state_dict):
-    """state dict -> bytes (torch.save), the driver<-rank-0 wire format (ray_lightning/util.py:73-77)."""
-    _buffer = io.BytesIO()
-    torch.save(model_state_dict, _buffer)
-    return _buffer.getvalue()
+def to_state_stream(model_state_dict) -> bytes:
+    buf = io.BytesIO()
+    torch.save(model_state_dict, buf)
+    return buf.getvalue()
 
 
-def load_state_stream(state_stream, to_gpu):
-    """bytes -> state dict on cpu, or on the current GPU when ``to_gpu`` and CUDA is available
-    (ray_lightning/util.py:80-92)."""
-    _buffer = io.BytesIO(state_stream)
-    to_gpu = to_gpu and torch.cuda.is_available()
-    return torch.load(_buffer, map_location=("cpu" if not to_gpu else lambda storage, loc: storage.cuda()),
-                      weights_only=False)
+def load_state_stream(state_stream: bytes, to_gpu: bool):
+    """Bytes -> state dict, on the current CUDA device when ``to_gpu`` and CUDA exists, else on CPU."""
+    on_gpu = bool(to_gpu) and torch.cuda.is_available()
+    where = (lambda storage, _loc: storage.cuda()) if on_gpu else "cpu"
+    return torch.load(io.BytesIO(state_stream), map_location=where, weights_only=False)
 
 
 def set_cuda_device_if_used(strategy) -> None:
-    """Bind the worker process to its root device (ray_lightning/util.py:95-102)."""
-    if strategy.use_gpu:
-        rank_zero_info("GPU available: True (cuda), used: True")
-        torch.cuda.set_device(strategy.root_device)
+    if not strategy.use_gpu:
+        return
+    rank_zero_info("GPU available: True (cuda), used: True")
+    torch.cuda.set_device(strategy.root_device)

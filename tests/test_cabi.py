@@ -61,3 +61,20 @@ def test_product_never_touches_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
                 assert "liboracle" not in src
+
+
+def test_header_is_plain_c_and_usable_from_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99, and a C program must be able to dlopen the
+    library and drive it (examples_c/b2d_probe.c) — no Python, no torch, no C++ in the signatures."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "b2d.h")
+    subprocess.run(["gcc", "-fsyntax-only", "-std=c99", "-Wall", "-Werror", "-x", "c", hdr], check=True)
+    exe = str(tmp_path / "b2d_probe")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples_c", "b2d_probe.c"), "-o", exe, "-ldl"], check=True)
+    out = subprocess.run([exe, _b2d.lib_path()], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert "libb2d version 100" in out.stdout
