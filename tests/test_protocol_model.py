@@ -107,3 +107,77 @@ def test_monotone_epochs_make_one_flag_set_enough_for_waiting():
     """With `>=` comparison a single flag set never blocks forever nor lets a rank through early: the data
     checks still hold (this is the scheme the split arrive/wait helpers rely on)."""
     assert explore(2, 3, halves=2, flag_sets=1) is None
+
+
+def explore_sharded(world, steps, grad_halves=2, gather_barrier=True, max_states=3_000_000):
+    """Same exploration for the fused sharded step (k456_sharded_kernel): gradients staged in a double
+    buffer, parameters SINGLE buffered in the symmetric arena.  Step k of rank r:
+        stage grads(k) -> barrier -> reduce peers' grads(k), Adam: params[r] := k -> barrier -> read params[p] == k.
+    The claim checked: no trailing barrier is needed, because rank r rewrites params[r] for step k+1 only after
+    the first barrier of step k+1, which every peer reaches only after its gather of step k."""
+
+    def program(k):
+        e1, e2 = 2 * k + 1, 2 * k + 2
+        pr = [("stage", k), ("arrive", e1)] + [("wait", (e1, p)) for p in range(world)]
+        pr += [("reduce_read", (k, p)) for p in range(world)] + [("adam", k)]
+        if gather_barrier:
+            pr += [("arrive", e2)] + [("wait", (e2, p)) for p in range(world)]
+        pr += [("gather_read", (k, p)) for p in range(world) ]
+        return pr
+
+    flat = [op for k in range(steps) for op in program(k)]
+    n_ops = len(flat)
+    init = (tuple([0] * world), tuple(tuple([-1] * grad_halves) for _ in range(world)), tuple([-1] * world),
+            tuple(tuple(tuple([0] * world) for _ in range(2)) for _ in range(world)))
+    seen, todo = {init}, deque([init])
+    while todo:
+        pcs, grads, params, flags = todo.popleft()
+        moved = False
+        for r in range(world):
+            pc = pcs[r]
+            if pc == n_ops:
+                continue
+            op, arg = flat[pc]
+            ng, npar, nf = grads, params, flags
+            if op == "stage":
+                row = list(grads[r]); row[arg % grad_halves] = arg
+                ng = grads[:r] + (tuple(row),) + grads[r + 1:]
+            elif op == "adam":
+                npar = params[:r] + (arg,) + params[r + 1:]
+            elif op == "arrive":
+                fl = [list(map(list, f)) for f in flags]
+                for p in range(world):
+                    fl[p][arg % 2][r] = arg
+                nf = tuple(tuple(tuple(x) for x in f) for f in fl)
+            elif op == "wait":
+                e, p = arg
+                if flags[r][e % 2][p] < e:
+                    continue
+            elif op == "reduce_read":
+                k, p = arg
+                if grads[p][k % grad_halves] != k:
+                    return "rank %d reduces step %d but sees gradient version %d of rank %d" % (r, k, grads[p][k % grad_halves], p)
+            elif op == "gather_read":
+                k, p = arg
+                if p != r and params[p] != k:
+                    return "rank %d gathers step %d but sees parameter version %d of rank %d" % (r, k, params[p], p)
+            moved = True
+            nxt = (pcs[:r] + (pc + 1,) + pcs[r + 1:], ng, npar, nf)
+            if nxt not in seen:
+                seen.add(nxt)
+                if len(seen) > max_states:
+                    raise RuntimeError("state space larger than expected")
+                todo.append(nxt)
+        if not moved and any(pc != n_ops for pc in pcs):
+            return "deadlock at program counters %r" % (pcs,)
+    return None
+
+
+@pytest.mark.parametrize("world,steps", [(2, 4), (3, 3)])
+def test_fused_sharded_step_needs_no_trailing_barrier(world, steps):
+    assert explore_sharded(world, steps) is None
+
+
+def test_the_sharded_model_catches_a_missing_gather_barrier():
+    bad = explore_sharded(2, 2, gather_barrier=False)
+    assert bad is not None and "parameter version" in bad
