@@ -228,9 +228,16 @@ class ActorHandle:
         self._pending = {}
         self._dead = False
         self._lock = threading.RLock()
-        ctx = mp.get_context("spawn")
+        wants_gpu = float(req.get("GPU", 0) or 0) > 0
+        # GPU workers get a pristine interpreter (spawn).  CPU-only workers come from a fork server that has
+        # torch imported already: same isolation, but the multi-second import is paid once per driver.
+        if wants_gpu or os.environ.get("B2D_ACTOR_START", "") == "spawn":
+            ctx = mp.get_context("spawn")
+        else:
+            ctx = mp.get_context("forkserver")
+            ctx.set_forkserver_preload(["torch", "cloudpickle", "numpy"])
         self._conn, child = ctx.Pipe(duplex=True)
-        env = {"CUDA_VISIBLE_DEVICES": ",".join(gpu_ids)} if float(req.get("GPU", 0) or 0) > 0 else {}
+        env = {"CUDA_VISIBLE_DEVICES": ",".join(gpu_ids)} if wants_gpu else {}
         self._proc = ctx.Process(target=_actor_main, args=(child, cloudpickle.dumps(cls), cloudpickle.dumps((args, kwargs)),
                                                            env, gpu_ids), daemon=True)
         self._proc.start()
