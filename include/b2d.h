@@ -92,7 +92,9 @@ typedef enum b2d_algo {
 
 int b2d_version(void);
 
-/* Create the per-rank context on CUDA device `device` (index inside the process's
+/* Replaces: the NCCL communicator bring-up hidden behind init_process_group("nccl") at
+ * ray_lightning/ray_ddp.py:192-196 (the process group itself stays, as control plane).
+ * Create the per-rank context on CUDA device `device` (index inside the process's
  * CUDA_VISIBLE_DEVICES, i.e. RayStrategy.root_device.index, ray_ddp.py:259-304) and
  * allocate its symmetric arena (`arena_bytes`, rounded up to 2 MiB) and signal pad.
  * Several contexts may live in one process (also on the same device: "loopback"
@@ -100,7 +102,10 @@ int b2d_version(void);
 int b2d_ctx_create(int rank, int world, int device, size_t arena_bytes,
                    unsigned flags, b2d_ctx** out);
 
-/* Write this rank's B2D_HANDLE_BYTES-byte handle blob.  The blob travels to the peers
+/* Replaces: NCCL's out-of-band ncclUniqueId / peer discovery, done for the reference inside
+ * init_process_group (ray_ddp.py:192-196); needs every worker to see its node's GPUs, which
+ * ray_lightning/launchers/ray_launcher.py:177-219 (_share_cuda_visible_devices) provides.
+ * Write this rank's B2D_HANDLE_BYTES-byte handle blob.  The blob travels to the peers
  * over whatever control plane the host already has (torch.distributed
  * all_gather_object, the Ray object store, ...).  For B2D_FLAG_MEM_VMM contexts the
  * blob additionally names a POSIX file descriptor (b2d_ctx_export_fd) that the host
@@ -116,7 +121,8 @@ int b2d_ctx_import(b2d_ctx* ctx, int peer, const void* handle_buf, size_t len);
  * control-plane barrier between the last b2d_ctx_finalize() and the first data call. */
 int b2d_ctx_finalize(b2d_ctx* ctx);
 
-/* NVLS (NVLink-SHARP multicast), optional: rank 0 creates the multicast object and
+/* Replaces: NCCL's own NVLS set-up (no reference line: NCCL decides it internally).
+ * NVLS (NVLink-SHARP multicast), optional: rank 0 creates the multicast object and
  * exports its fd; every rank (rank 0 included) joins with the fd, then — after a
  * control-plane barrier — binds its arena.  Returns B2D_ERR_UNSUPPORTED when the
  * device or driver does not expose multicast. */
@@ -137,7 +143,13 @@ int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes); /* AUTO: on
 
 /* ---- data path ------------------------------------------------------------------------- */
 
-/* In-place allreduce of one DDP gradient bucket (K0/K1/K2/K3).
+/* Replaces: the per-bucket collective torch DDP issues for RayStrategy(**ddp_kwargs)
+ * (ray_lightning/ray_ddp.py:75,112-116) — with B2D_WIRE_BF16 the whole bf16_compress_hook
+ * (torch/distributed/algorithms/ddp_comm_hooks/default_hooks.py:57-93,116-134: cast, div,
+ * ncclAllReduce, copy_), with B2D_WIRE_FP32 the default divide + allreduce
+ * (default_hooks.py:18-54, default_comm_hooks.hpp:36-51).  Called from the DDP comm hook
+ * (torch/nn/parallel/distributed.py:1987-2067).
+ * In-place allreduce of one DDP gradient bucket (K0/K1/K2/K2T/K3).
  *   grad_inout : this rank's flat fp32 bucket (GradBucket.buffer(), comm.hpp:20-98), n elements
  *   bucket_idx : GradBucket.index(); selects the arena slot (double-buffered, so no
  *                trailing barrier is needed between consecutive steps)
@@ -156,7 +168,11 @@ typedef struct b2d_adam {
   int32_t zero_grads; /* 1: overwrite the local flat grads with 0 once they are staged */
 } b2d_adam;
 
-/* Sharded optimizer step (K4+K5+K6 fused): the flat fp32 gradient space [0, n) is cut
+/* Replaces: what RayShardedStrategy (ray_lightning/ray_ddp_sharded.py:12-13) reaches through PL's
+ * DDPSpawnShardedStrategy: FairScale ShardedDataParallel's reduce-to-owner of every gradient,
+ * OSS.step() on the owned shard and OSS._broadcast_params() (torch analogue:
+ * torch/distributed/optim/zero_redundancy_optimizer.py:759-825,1038-1142).
+ * Sharded optimizer step (K4+K5+K6 fused): the flat fp32 gradient space [0, n) is cut
  * into `world` contiguous owner shards shard_off[r] .. shard_off[r+1] (element offsets,
  * world+1 entries, multiples of 8, parameter aligned — FairScale OSS.partition_parameters
  * ownership).  Rank r: reduces its shard from all peers (x scale), applies Adam to
@@ -169,17 +185,20 @@ int b2d_sharded_step(b2d_ctx* ctx, int slot, const float* grads, float* params,
                      const int64_t* shard_off, int wire, float scale,
                      const b2d_adam* adam, void* wait_stream, void* comm_stream);
 
-/* K4 alone: out[0 .. len_r) = sum_r grads_r[shard_off[rank] ..) * scale  (fp32 out, local). */
+/* Replaces: FairScale's dist.reduce(grad, dst=owner) stream for optimizers other than Adam/AdamW.
+ * K4 alone: out[0 .. len_r) = sum_r grads_r[shard_off[rank] ..) * scale  (fp32 out, local). */
 int b2d_reduce_scatter(b2d_ctx* ctx, int slot, const float* grads, float* out, size_t n,
                        const int64_t* shard_off, int wire, float scale,
                        void* wait_stream, void* comm_stream);
 
-/* K6 alone: `buf` (flat fp32 [n], in the arena) holds this rank's valid shard; pull every
+/* Replaces: OSS._broadcast_params (one broadcast per owner) after a local optimizer step.
+ * K6 alone: `buf` (flat fp32 [n], in the arena) holds this rank's valid shard; pull every
  * other shard from its owner. */
 int b2d_allgather(b2d_ctx* ctx, float* buf, size_t n, const int64_t* shard_off,
                   void* wait_stream, void* comm_stream);
 
-/* All-ranks barrier enqueued on `stream` (also quiesces the arena before slots are re-laid out). */
+/* Replaces: nothing in the reference (dist.barrier is host side); device-side fence of this library.
+ * All-ranks barrier enqueued on `stream` (also quiesces the arena before slots are re-laid out). */
 int b2d_barrier(b2d_ctx* ctx, void* stream);
 
 /* ---- symmetric arena ------------------------------------------------------------------- */
