@@ -79,8 +79,10 @@ typedef enum b2d_algo {
   B2D_ALGO_ONE_SHOT = 1,   /* every rank reads every peer's whole staged bucket */
   B2D_ALGO_TWO_SHOT = 2,   /* reduce-scatter of 1/W slices + all-gather, both by peer reads */
   B2D_ALGO_NVLS = 3,       /* multimem.ld_reduce / multimem.st through the NVSwitch */
-  B2D_ALGO_TWO_SHOT_TMA = 4 /* two-shot with every load a TMA bulk copy into a shared-memory ring (bf16 wire,
+  B2D_ALGO_TWO_SHOT_TMA = 4, /* two-shot with every load a TMA bulk copy into a shared-memory ring (bf16 wire,
                                n % 8 == 0; other shapes fall back to B2D_ALGO_TWO_SHOT) */
+  B2D_ALGO_TWO_SHOT_PIPE = 5, /* EXPERIMENTAL role-decoupled chunk pipeline (world 2/4/8; else falls back) */
+  B2D_ALGO_NVLS_PIPE = 6      /* EXPERIMENTAL the same pipeline with multimem.ld_reduce / multimem.st */
 } b2d_algo;
 
 /* b2d_ctx_create flags */

@@ -15,12 +15,12 @@ MAX_WORLD = 8
 MAX_BLOCKS = 296
 
 WIRE_FP32, WIRE_BF16 = 0, 1
-ALGO_AUTO, ALGO_ONE_SHOT, ALGO_TWO_SHOT, ALGO_NVLS, ALGO_TWO_SHOT_TMA = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_ONE_SHOT, ALGO_TWO_SHOT, ALGO_NVLS, ALGO_TWO_SHOT_TMA, ALGO_TWO_SHOT_PIPE, ALGO_NVLS_PIPE = 0, 1, 2, 3, 4, 5, 6
 FLAG_MEM_LEGACY_IPC, FLAG_MEM_VMM, FLAG_TIMING = 0x0, 0x1, 0x2
 
 WIRE_NAMES = {"fp32": WIRE_FP32, "bf16": WIRE_BF16}
 ALGO_NAMES = {"auto": ALGO_AUTO, "one_shot": ALGO_ONE_SHOT, "two_shot": ALGO_TWO_SHOT, "nvls": ALGO_NVLS,
-              "two_shot_tma": ALGO_TWO_SHOT_TMA}
+              "two_shot_tma": ALGO_TWO_SHOT_TMA, "two_shot_pipe": ALGO_TWO_SHOT_PIPE, "nvls_pipe": ALGO_NVLS_PIPE}
 
 # every symbol include/b2d.h declares (checked by tests/test_cabi.py on a GPU-less box)
 EXPORTED_SYMBOLS = [

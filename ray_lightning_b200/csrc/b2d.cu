@@ -18,6 +18,7 @@
 
 #include "b2d_kernels.cuh"
 #include "b2d_tma.cuh"
+#include "b2d_pipe.cuh"
 
 using namespace b2d;
 
@@ -185,6 +186,7 @@ struct b2d_ctx {
   int max_ctas = 64;
   int tma_ctas = 48;        // CTAs of the TMA-staged kernel (b2d_ctx_set_max_ctas caps it too)
   int tma_ctas_user = 0;
+  int pipe_runs_per_chunk = 4;   // K2P: runs of 128 packs per chunk and block
   size_t one_shot_max_bytes = 1024 * 1024;
   unsigned timeout_ms = 10000;
   int last_algo = 0, last_grid = 0, last_block = 0;
@@ -341,6 +343,8 @@ int launch_barrier(b2d_ctx* ctx, cudaStream_t stream) {
 int pick_algo(b2d_ctx* ctx, size_t n, int wire, int algo) {
   if (ctx->world == 1) return B2D_ALGO_ONE_SHOT;
   if (algo == B2D_ALGO_TWO_SHOT_TMA && (wire != B2D_WIRE_BF16 || n % 8 != 0)) return B2D_ALGO_TWO_SHOT;
+  if ((algo == B2D_ALGO_TWO_SHOT_PIPE || algo == B2D_ALGO_NVLS_PIPE) && ctx->world != 2 && ctx->world != 4 && ctx->world != 8)
+    return algo == B2D_ALGO_NVLS_PIPE ? B2D_ALGO_NVLS : B2D_ALGO_TWO_SHOT;
   if (algo != B2D_ALGO_AUTO) return algo;
   const size_t wire_bytes = n * (wire == B2D_WIRE_BF16 ? 2 : 4);
   // at world 2 one-shot moves exactly the two-shot's bytes with one barrier less
@@ -362,6 +366,13 @@ int tma_mt(size_t slice, int grid) {
 int pick_grid(b2d_ctx* ctx, size_t n, int wire, int algo) {
   const size_t epp = wire == B2D_WIRE_BF16 ? 8 : 4;
   const size_t npacks = (n + epp - 1) / epp;
+  if (algo == B2D_ALGO_TWO_SHOT_PIPE || algo == B2D_ALGO_NVLS_PIPE) {
+    const size_t slice = (npacks + ctx->world - 1) / ctx->world;
+    size_t grid = (slice + kPipeRun - 1) / kPipeRun;   // at least one run per block
+    if (grid < 1) grid = 1;
+    if (grid > static_cast<size_t>(ctx->max_ctas)) grid = ctx->max_ctas;
+    return static_cast<int>(grid);
+  }
   if (algo == B2D_ALGO_TWO_SHOT_TMA) {
     const size_t slice = (npacks + ctx->world - 1) / ctx->world;
     size_t grid = (slice + 255) / 256;   // at least 4 KiB of wire per block and slice
@@ -455,12 +466,20 @@ void preload_world() {
   preload_one(k456_sharded_kernel<W, false>);
 }
 template <int W>
+void preload_pipe() {
+  preload_one(k2p_two_shot_pipe_kernel<W, true, false>);
+  preload_one(k2p_two_shot_pipe_kernel<W, true, true>);
+  preload_one(k2p_two_shot_pipe_kernel<W, false, false>);
+  preload_one(k2p_two_shot_pipe_kernel<W, false, true>);
+}
+template <int W>
 void tma_attr() {
   if (cudaFuncSetAttribute(k2t_two_shot_tma_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes) != cudaSuccess)
     cudaGetLastError();
 }
 void preload_kernels() {
   tma_attr<0>(); tma_attr<2>(); tma_attr<4>(); tma_attr<8>();
+  preload_pipe<2>(); preload_pipe<4>(); preload_pipe<8>();
   preload_one(k0_cast_scale_kernel<true>);
   preload_one(k0_cast_scale_kernel<false>);
   preload_one(barrier_kernel);
@@ -882,7 +901,8 @@ int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, in
   if (grad == nullptr && n != 0) return fail(ctx, B2D_ERR_INVALID, "grad is NULL");
   if (reinterpret_cast<uintptr_t>(grad) % 16 != 0) return fail(ctx, B2D_ERR_INVALID, "bucket buffer must be 16-byte aligned");
   if (wire != B2D_WIRE_FP32 && wire != B2D_WIRE_BF16) return fail(ctx, B2D_ERR_INVALID, "bad wire %d", wire);
-  if (algo < B2D_ALGO_AUTO || algo > B2D_ALGO_TWO_SHOT_TMA) return fail(ctx, B2D_ERR_INVALID, "bad algo %d", algo);
+  if (algo < B2D_ALGO_AUTO || algo > B2D_ALGO_NVLS_PIPE) return fail(ctx, B2D_ERR_INVALID, "bad algo %d", algo);
+  if (algo == B2D_ALGO_NVLS_PIPE && !ctx->mc_bound && ctx->world > 1) return fail(ctx, B2D_ERR_UNSUPPORTED, "NVLS requested but no multicast object is bound");
   if (algo == B2D_ALGO_NVLS && !ctx->mc_bound && ctx->world > 1) return fail(ctx, B2D_ERR_UNSUPPORTED, "NVLS requested but no multicast object is bound");
   if (n == 0) return B2D_OK;  // empty bucket: nothing to exchange, and every rank agrees on that
   DeviceGuard guard(ctx->device);
@@ -928,6 +948,23 @@ int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, in
     case B2D_ALGO_NVLS:
       if (bf) launch_two_shot<true, true>(P, ctx->world, grid, comm); else launch_two_shot<false, true>(P, ctx->world, grid, comm);
       break;
+    case B2D_ALGO_TWO_SHOT_PIPE:
+    case B2D_ALGO_NVLS_PIPE: {
+      const int K = ctx->pipe_runs_per_chunk;
+      const bool nv = a == B2D_ALGO_NVLS_PIPE;
+#define B2D_PIPE(WW)                                                                                   \
+      if (bf) { if (nv) k2p_two_shot_pipe_kernel<WW, true, true><<<grid, kThreads, 0, comm>>>(P, K);     \
+                else k2p_two_shot_pipe_kernel<WW, true, false><<<grid, kThreads, 0, comm>>>(P, K); }   \
+      else    { if (nv) k2p_two_shot_pipe_kernel<WW, false, true><<<grid, kThreads, 0, comm>>>(P, K);    \
+                else k2p_two_shot_pipe_kernel<WW, false, false><<<grid, kThreads, 0, comm>>>(P, K); }
+      switch (ctx->world) {
+        case 2: B2D_PIPE(2) break;
+        case 4: B2D_PIPE(4) break;
+        default: B2D_PIPE(8) break;
+      }
+#undef B2D_PIPE
+      break;
+    }
     case B2D_ALGO_TWO_SHOT_TMA: {
       const int mt = tma_mt(slice, grid);
       switch (ctx->world) {

@@ -31,9 +31,13 @@ namespace b2d {
 struct Signal {
   uint32_t flag[2][B2D_MAX_BLOCKS][B2D_MAX_WORLD];
   uint32_t ctr[B2D_MAX_BLOCKS];
+  // K2P (b2d_pipe.cuh): monotone chunk counters, written by rank `src`'s block, and the local base
+  uint32_t cntA[B2D_MAX_BLOCKS][B2D_MAX_WORLD];   // chunks staged so far (cumulative over kernel calls)
+  uint32_t cntB[B2D_MAX_BLOCKS][B2D_MAX_WORLD];   // chunks reduced so far
+  uint32_t pbase[B2D_MAX_BLOCKS];                 // own cumulative chunk count at kernel start (local only)
 };
-static_assert(sizeof(Signal) <= 32 * 1024, "signal pad must fit its 32 KiB reservation");
-constexpr size_t kSignalBytes = 32 * 1024;
+static_assert(sizeof(Signal) <= 64 * 1024, "signal pad must fit its 64 KiB reservation");
+constexpr size_t kSignalBytes = 64 * 1024;
 
 // Written (host-mapped pinned memory) by a block that gives up waiting for a peer.
 struct Diag {

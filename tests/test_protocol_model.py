@@ -181,3 +181,116 @@ def test_fused_sharded_step_needs_no_trailing_barrier(world, steps):
 def test_the_sharded_model_catches_a_missing_gather_barrier():
     bad = explore_sharded(2, 2, gather_barrier=False)
     assert bad is not None and "parameter version" in bad
+
+
+def explore_pipelined(world, steps, chunks, halves=2, kernel_join=True, max_states=4_000_000):
+    """Role-decoupled chunk pipeline (the K2P design): per rank three concurrent roles coupled only by
+    monotone per-role counters — S stages chunk c and publishes cntA = base+c+1; R waits cntA of ALL ranks,
+    reduces chunk c of its slice in place, publishes cntB; G waits cntB of all ranks and gathers chunk c.
+    A kernel call ends when all three roles of the rank are done (join); consecutive calls alternate halves.
+    Checked: every read sees (kind, step) it expects; no deadlock."""
+    # per (rank, role) program for step k: list of ops
+    def prog_S(k):
+        return [x for c in range(chunks) for x in (("stage", (k, c)), ("pubA", k * chunks + c + 1))]
+
+    def prog_R(k):
+        return [x for c in range(chunks) for x in (("waitA", k * chunks + c + 1), ("reduce", (k, c)), ("pubB", k * chunks + c + 1))]
+
+    def prog_G(k):
+        return [x for c in range(chunks) for x in (("waitB", k * chunks + c + 1), ("gather", (k, c)))]
+
+    progs = {"S": prog_S, "R": prog_R, "G": prog_G}
+    roles = ("S", "R", "G")
+    # state: step[rank], pc[rank][role], mem[rank][half][chunk][slice]=(kind,step), cntA[rank][src], cntB[rank][src]
+    empty = (-1, -1)
+    mem0 = tuple(tuple(tuple(tuple([empty] * world) for _ in range(chunks)) for _ in range(halves)) for _ in range(world))
+    zero = tuple(tuple([0] * world) for _ in range(world))
+    init = (tuple([0] * world), tuple((0, 0, 0) for _ in range(world)), mem0, zero, zero)
+    seen, todo = {init}, deque([init])
+    lens = {r: len(progs[r](0)) for r in roles}
+
+    def setmem(mem, p, h, c, sl, val):
+        m = [[[list(x) for x in ch] for ch in hf] for hf in mem]
+        if sl is None:
+            m[p][h][c] = [val] * world
+        else:
+            m[p][h][c][sl] = val
+        return tuple(tuple(tuple(tuple(x) for x in ch) for ch in hf) for hf in m)
+
+    while todo:
+        stepv, pcs, mem, cntA, cntB = todo.popleft()
+        moved = False
+        done_all = True
+        for r in range(world):
+            k = stepv[r]
+            if k == steps:
+                continue
+            done_all = False
+            # kernel join: next step starts only when all three roles finished this one
+            if all(pcs[r][i] == lens[roles[i]] for i in range(3)):
+                nstep = stepv[:r] + (k + 1,) + stepv[r + 1:]
+                npcs = pcs[:r] + ((0, 0, 0),) + pcs[r + 1:]
+                nxt = (nstep, npcs, mem, cntA, cntB)
+                moved = True
+                if nxt not in seen:
+                    seen.add(nxt); todo.append(nxt)
+                continue
+            for ri, role in enumerate(roles):
+                pc = pcs[r][ri]
+                if pc == lens[role]:
+                    continue
+                if not kernel_join:
+                    pass
+                op, arg = progs[role](k)[pc]
+                nmem, nA, nB = mem, cntA, cntB
+                if op == "stage":
+                    kk, c = arg
+                    nmem = setmem(mem, r, kk % halves, c, None, (0, kk))
+                elif op == "pubA":
+                    a = [list(x) for x in cntA]
+                    for p in range(world):
+                        a[p][r] = arg
+                    nA = tuple(tuple(x) for x in a)
+                elif op == "pubB":
+                    b = [list(x) for x in cntB]
+                    for p in range(world):
+                        b[p][r] = arg
+                    nB = tuple(tuple(x) for x in b)
+                elif op == "waitA":
+                    if any(cntA[r][p] < arg for p in range(world)):
+                        continue
+                elif op == "waitB":
+                    if any(cntB[r][p] < arg for p in range(world)):
+                        continue
+                elif op == "reduce":
+                    kk, c = arg
+                    for p in range(world):
+                        if mem[p][kk % halves][c][r] != (0, kk):
+                            return "rank %d reduces (step %d, chunk %d) but rank %d holds %r" % (r, kk, c, p, mem[p][kk % halves][c][r])
+                    nmem = setmem(mem, r, kk % halves, c, r, (1, kk))
+                elif op == "gather":
+                    kk, c = arg
+                    for p in range(world):
+                        if mem[p][kk % halves][c][p] != (1, kk):
+                            return "rank %d gathers (step %d, chunk %d) but rank %d holds %r" % (r, kk, c, p, mem[p][kk % halves][c][p])
+                moved = True
+                row = list(pcs[r]); row[ri] = pc + 1
+                nxt = (stepv, pcs[:r] + (tuple(row),) + pcs[r + 1:], nmem, nA, nB)
+                if nxt not in seen:
+                    seen.add(nxt)
+                    if len(seen) > max_states:
+                        raise RuntimeError("state space larger than expected")
+                    todo.append(nxt)
+        if not moved and not done_all:
+            return "deadlock at steps %r pcs %r" % (stepv, pcs)
+    return None
+
+
+@pytest.mark.parametrize("world,steps,chunks", [(2, 3, 2), (2, 2, 3), (3, 2, 2)])
+def test_role_decoupled_chunk_pipeline_is_safe(world, steps, chunks):
+    assert explore_pipelined(world, steps, chunks) is None
+
+
+def test_pipelined_model_catches_single_buffering():
+    bad = explore_pipelined(2, 3, 2, halves=1)
+    assert bad is not None and "holds" in bad
