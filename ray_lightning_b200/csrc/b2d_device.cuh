@@ -10,8 +10,12 @@
 // (8 bf16 or 4 fp32 gradient elements).
 #pragma once
 
+#ifdef B2D_EMU   // CPU emulation of the device environment: tests only (csrc/emu/cuda_emu.h)
+#include "emu/cuda_emu.h"
+#else
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/b2d.h"
@@ -52,6 +56,49 @@ struct Peers {
 };
 
 // ---- memory ops ------------------------------------------------------------------------
+#ifdef B2D_EMU
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) { return emu_ld128(p); }
+__device__ __forceinline__ uint4 ld_peer_v4(const void* p) { return emu_ld128(p); }
+__device__ __forceinline__ void st_v4(void* p, const uint4& v) { emu_st128(p, v); }
+__device__ __forceinline__ void st_stream_v4(void* p, const uint4& v) { emu_st128(p, v); }
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) { return emu_ld32(p); }
+__device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) { emu_st32(p, v); }
+__device__ __forceinline__ unsigned long long global_timer_ns() { return emu_timer_ns(); }
+// NVLS: the "switch" adds the 8 bf16 lanes (or 4 fp32) of every bound arena in fp32, in rank order
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc_ptr) {
+  const emu::Multicast& m = emu::multicast();
+  const size_t off = static_cast<const unsigned char*>(mc_ptr) - m.fake_base;
+  float acc[8];
+  for (int r = 0; r < m.world; ++r) {
+    const uint4 v = emu_ld128(m.arena[r] + off);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int k = 0; k < 4; ++k) {
+      const float lo = emu_bf16_to_f32(static_cast<uint16_t>(w[k] & 0xffffu)), hi = emu_bf16_to_f32(static_cast<uint16_t>(w[k] >> 16));
+      acc[2 * k] = r == 0 ? lo : __fadd_rn(acc[2 * k], lo);
+      acc[2 * k + 1] = r == 0 ? hi : __fadd_rn(acc[2 * k + 1], hi);
+    }
+  }
+  uint32_t o[4];
+  for (int k = 0; k < 4; ++k) o[k] = static_cast<uint32_t>(emu_f32_to_bf16(acc[2 * k])) | (static_cast<uint32_t>(emu_f32_to_bf16(acc[2 * k + 1])) << 16);
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ uint4 multimem_ld_reduce_f32x4(const void* mc_ptr) {
+  const emu::Multicast& m = emu::multicast();
+  const size_t off = static_cast<const unsigned char*>(mc_ptr) - m.fake_base;
+  float acc[4];
+  for (int r = 0; r < m.world; ++r) {
+    const uint4 v = emu_ld128(m.arena[r] + off);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int k = 0; k < 4; ++k) acc[k] = r == 0 ? __uint_as_float(w[k]) : __fadd_rn(acc[k], __uint_as_float(w[k]));
+  }
+  return make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+}
+__device__ __forceinline__ void multimem_st_v4(void* mc_ptr, const uint4& v) {
+  const emu::Multicast& m = emu::multicast();
+  const size_t off = static_cast<unsigned char*>(mc_ptr) - m.fake_base;
+  for (int r = 0; r < m.world; ++r) emu_st128(m.arena[r] + off, v);
+}
+#else
 // Own fp32 gradients: streamed once, keep them out of L1.
 __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
   uint4 r;
@@ -122,16 +169,28 @@ __device__ __forceinline__ void multimem_st_v4(void* mc_ptr, const uint4& v) {
                : "memory");
 }
 
+#endif  // B2D_EMU
+
 // ---- number formats --------------------------------------------------------------------
+#ifdef B2D_EMU
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  return static_cast<uint32_t>(emu_f32_to_bf16(lo)) | (static_cast<uint32_t>(emu_f32_to_bf16(hi)) << 16);
+}
+#else
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);  // cvt.rn.bf16x2.f32: RNE, NaN kept
   return *reinterpret_cast<uint32_t*>(&b);
 }
+#endif
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 // fp32 -> bf16 -> fp32 (what `t.to(torch.bfloat16)` keeps of a value)
 __device__ __forceinline__ float round_bf16(float x) {
+#ifdef B2D_EMU
+  return emu_bf16_to_f32(emu_f32_to_bf16(x));
+#else
   return __bfloat162float(__float2bfloat16_rn(x));
+#endif
 }
 // bf16_compress_hook prologue for one element: `buffer.to(bf16).div_(world)`.  torch's CUDA
 // div-by-scalar multiplies by the fp32 reciprocal and rounds once more to bf16, so the value

@@ -1,0 +1,128 @@
+"""The libb2d KERNEL SOURCES, compiled for the host and executed on CPU threads (one OS thread per CUDA
+thread, all ranks of a job concurrently in one process), checked bit for bit against the oracle.
+
+This is not a CPU fallback of the product — csrc/emu/ is test infrastructure that only this file builds — it is
+a way to execute the real index mappings, phase structure, per-block epoch barriers and double buffering of
+b2d_kernels.cuh without a GPU, under whatever interleaving the OS scheduler produces.  It cannot see GPU memory-
+ordering bugs or performance; the `-m gpu` tests and the model in test_protocol_model.py cover those angles."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import ddp_oracle
+
+EMU_DIR = os.path.join(ROOT, "ray_lightning_b200", "csrc", "emu")
+FP = ctypes.POINTER(ctypes.c_float)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "libb2d_emu.so")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DB2D_EMU", "-ffp-contract=off",
+                    "-o", out, os.path.join(EMU_DIR, "emu_harness.cpp")], check=True)
+    lib = ctypes.CDLL(out)
+    lib.emu_group_create.restype = ctypes.c_void_p
+    lib.emu_group_create.argtypes = [ctypes.c_int, ctypes.c_size_t]
+    lib.emu_group_destroy.argtypes = [ctypes.c_void_p]
+    lib.emu_signal_bytes.restype = ctypes.c_size_t
+    lib.emu_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(FP), ctypes.c_size_t,
+                                  ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.emu_k0.argtypes = [FP, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_int]
+    lib.emu_sharded_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(FP), ctypes.c_size_t, ctypes.POINTER(FP),
+                                     ctypes.POINTER(FP), ctypes.c_size_t, ctypes.POINTER(ctypes.c_longlong), ctypes.c_float,
+                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.emu_arena_ptr.restype = FP
+    lib.emu_arena_ptr.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]
+    return lib
+
+
+def inputs(world, n, seed):
+    return [(torch.randn(n, generator=torch.Generator().manual_seed(1000 * seed + r)) * 2.0 ** -4) for r in range(world)]
+
+
+def ptrs(arrs):
+    return (FP * len(arrs))(*[a.ctypes.data_as(FP) for a in arrs])
+
+
+def same_bits(a, b):
+    return np.array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+
+
+@pytest.mark.parametrize("bf16", [1, 0])
+def test_k0_on_cpu_threads(emu, bf16):
+    for n in (1, 7, 1000, 4099):
+        x = inputs(1, n, 5)[0]
+        buf = x.numpy().copy()
+        assert emu.emu_k0(buf.ctypes.data_as(FP), n, 1.0, bf16, 2) == 0
+        want = (ddp_oracle.allreduce_bf16_wire if bf16 else ddp_oracle.allreduce_fp32_wire)([x])
+        assert same_bits(buf, want.numpy()), n
+
+
+@pytest.mark.parametrize("world,grid,generic", [(2, 2, 0), (4, 2, 0), (8, 1, 0), (3, 2, 1)])
+@pytest.mark.parametrize("algo", [1, 2, 3])
+def test_allreduce_kernels_on_cpu_threads(emu, world, grid, generic, algo):
+    """K1 (one-shot), K2 (two-shot) and K3 (NVLS, the switch emulated) for both wires; consecutive launches
+    alternate the slot half and keep the epoch counters, as in the real call sequence."""
+    g = emu.emu_group_create(world, 4 << 20)
+    try:
+        step = 0
+        for bf16 in (1, 0):
+            for n in (1, 9, 1000, 4099, 20011):
+                per_rank = inputs(world, n, 10 * step + algo)
+                bufs = [t.numpy().copy() for t in per_rank]
+                scale = float(np.float32(1.0) / np.float32(world))
+                assert emu.emu_allreduce(g, algo, bf16, ptrs(bufs), n, scale, grid, step & 1, generic, 4) == 0
+                want = (ddp_oracle.allreduce_bf16_wire if bf16 else ddp_oracle.allreduce_fp32_wire)(per_rank).numpy()
+                for r in range(world):
+                    assert same_bits(bufs[r], want), (world, algo, bf16, n, r)
+                step += 1
+    finally:
+        emu.emu_group_destroy(g)
+
+
+@pytest.mark.parametrize("world,generic", [(2, 0), (4, 0), (3, 1)])
+@pytest.mark.parametrize("bf16", [0, 1])
+def test_sharded_step_on_cpu_threads(emu, world, generic, bf16):
+    """K4+K5+K6: three consecutive fused steps; every rank ends with the same, whole parameter vector ==
+    Adam on the oracle-averaged gradients (uneven, 8-aligned owner shards)."""
+    rng = np.random.default_rng(3)
+    numels = [int(x) for x in rng.integers(1, 700, size=9)] + [3000]
+    owner = ddp_oracle.partition_fairscale(numels, world)
+    _, shard_off, total = ddp_oracle.shard_layout(numels, owner, world)
+    sig = emu.emu_signal_bytes()
+    g = emu.emu_group_create(world, 4 << 20)
+    try:
+        p0 = torch.randn(total, generator=torch.Generator().manual_seed(9))
+        views = []
+        for r in range(world):
+            v = np.ctypeslib.as_array(emu.emu_arena_ptr(g, r, sig), shape=(total,))
+            v[:] = p0.numpy()
+            views.append(v)
+        ms = [np.zeros(max(shard_off[r + 1] - shard_off[r], 8), np.float32) for r in range(world)]
+        vs = [np.zeros(max(shard_off[r + 1] - shard_off[r], 8), np.float32) for r in range(world)]
+        ref = torch.nn.Parameter(p0.clone())
+        opt = torch.optim.Adam([ref], lr=1e-2)
+        scale = float(np.float32(1.0) / np.float32(world))
+        off = (ctypes.c_longlong * (world + 1))(*shard_off)
+        for step in range(1, 4):
+            per_rank = [torch.randn(total, generator=torch.Generator().manual_seed(100 * step + r)) * 0.1 for r in range(world)]
+            grads = [t.numpy().copy() for t in per_rank]
+            rc = emu.emu_sharded_step(g, bf16, ptrs(grads), sig, ptrs(ms), ptrs(vs), total, off, scale, 1e-2, 0.9, 0.999, 1e-8,
+                                      0.0, step, 0, int(step == 2), 2, step & 1, generic)
+            assert rc == 0
+            avg = ddp_oracle.allreduce_fp32_wire(per_rank, scale) if not bf16 else sum(ddp_oracle.wire_bf16(t, scale) for t in per_rank)
+            ref.grad = avg.clone()
+            opt.step()
+            for r in range(1, world):
+                assert same_bits(views[r], views[0]), (step, r)
+            np.testing.assert_allclose(views[0], ref.detach().numpy(), rtol=2e-5, atol=2e-6)
+            if step == 2:
+                assert all(float(np.abs(gr).max()) == 0.0 for gr in grads)
+    finally:
+        emu.emu_group_destroy(g)
