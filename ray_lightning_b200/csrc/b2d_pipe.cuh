@@ -1,5 +1,10 @@
-// b2d_pipe.cuh — K2P: the two-shot allreduce as a role-decoupled chunk pipeline.   [EXPERIMENTAL: written after
-// the round-1 GPU budget was spent; NOT yet run on hardware, not reachable from AUTO — see DESIGN.md §9]
+// b2d_pipe.cuh — K2P: the two-shot allreduce as a role-decoupled chunk pipeline.
+//
+// STATUS: opt-in (`two_shot_pipe` = 5, `nvls_pipe` = 6), unreachable from AUTO.  Written after round 1's GPU
+// budget was spent: its logic is validated on CPU threads against the oracle (tests/test_kernel_emulation.py,
+// the very source below compiled for the host) and its protocol by exhaustive interleaving
+// (tests/test_protocol_model.py::explore_pipelined); it compiles for sm_100a (128 registers, 4 named
+// barriers) but has NOT run on hardware yet — tests/test_gpu_experimental.py is gated accordingly.
 //
 // Why: in K2 every phase already runs at its hardware limit (HBM 6.5 TB/s, NVLink ~790 GB/s) but the
 // phases run one after the other and each of the two barriers stalls the whole block for 10-60 us.  Here the
@@ -29,7 +34,11 @@ constexpr int kPipeTS = 160, kPipeTR = 160, kPipeTG = 192;   // threads per role
 static_assert(kPipeTS + kPipeTR + kPipeTG == kThreads, "roles must fill the block");
 
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
+#ifdef B2D_EMU
+  emu_named_barrier(id, nthreads);
+#else
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
 }
 
 // spin until *ptr >= target (wrap-safe); trap with diagnostics after timeout_ns

@@ -23,7 +23,7 @@ FP = ctypes.POINTER(ctypes.c_float)
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("emu") / "libb2d_emu.so")
-    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DB2D_EMU", "-ffp-contract=off",
+    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DB2D_EMU", "-DB2D_EMU_WITH_PIPE", "-ffp-contract=off",
                     "-o", out, os.path.join(EMU_DIR, "emu_harness.cpp")], check=True)
     lib = ctypes.CDLL(out)
     lib.emu_group_create.restype = ctypes.c_void_p
@@ -124,5 +124,28 @@ def test_sharded_step_on_cpu_threads(emu, world, generic, bf16):
             np.testing.assert_allclose(views[0], ref.detach().numpy(), rtol=2e-5, atol=2e-6)
             if step == 2:
                 assert all(float(np.abs(gr).max()) == 0.0 for gr in grads)
+    finally:
+        emu.emu_group_destroy(g)
+
+
+@pytest.mark.parametrize("world,grid", [(2, 2), (4, 2), (8, 1)])
+@pytest.mark.parametrize("algo", [5, 6])
+@pytest.mark.parametrize("pipe_k", [1, 2])
+def test_pipelined_kernel_on_cpu_threads(emu, world, grid, algo, pipe_k):
+    """K2P (three concurrent warp roles coupled by monotone counters), P2P and NVLS variants: several chunks per
+    block (run = 128 packs, chunk = pipe_k runs), ragged sizes, consecutive launches on alternating halves."""
+    g = emu.emu_group_create(world, 8 << 20)
+    try:
+        step = 0
+        for bf16 in (1, 0):
+            for n in (1, 9, 4099, 20011, 70001):
+                per_rank = inputs(world, n, 50 * step + algo)
+                bufs = [t.numpy().copy() for t in per_rank]
+                scale = float(np.float32(1.0) / np.float32(world))
+                assert emu.emu_allreduce(g, algo, bf16, ptrs(bufs), n, scale, grid, step & 1, 0, pipe_k) == 0
+                want = (ddp_oracle.allreduce_bf16_wire if bf16 else ddp_oracle.allreduce_fp32_wire)(per_rank).numpy()
+                for r in range(world):
+                    assert same_bits(bufs[r], want), (world, algo, bf16, n, r, pipe_k)
+                step += 1
     finally:
         emu.emu_group_destroy(g)
