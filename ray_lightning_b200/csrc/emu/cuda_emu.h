@@ -71,8 +71,21 @@ inline Multicast& multicast() {
 extern thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 extern thread_local emu::Block* emu_block;
 
-inline void __syncthreads() { emu_block->bar0.arrive_and_wait(); }
-inline void emu_named_barrier(int id, int count) { emu_block->get_named(id, count).arrive_and_wait(); }
+// B2D_EMU_JITTER=<permille>: every barrier entry sleeps a random 0-300 us with that probability, so that
+// roles / blocks / ranks drift apart far more than the scheduler alone would make them (straggler stress)
+inline void emu_jitter() {
+  const char* e = std::getenv("B2D_EMU_JITTER");   // read per call: tests switch it on and off within one process
+  const int permille = e ? std::atoi(e) : 0;
+  if (permille <= 0) return;
+  thread_local uint32_t state = 0x9e3779b9u ^ static_cast<uint32_t>(reinterpret_cast<uintptr_t>(&state));
+  state = state * 1664525u + 1013904223u;
+  if (static_cast<int>((state >> 16) % 1000u) < permille) {
+    timespec ts{0, static_cast<long>((state >> 8) % 300u) * 1000L};
+    nanosleep(&ts, nullptr);
+  }
+}
+inline void __syncthreads() { emu_jitter(); emu_block->bar0.arrive_and_wait(); }
+inline void emu_named_barrier(int id, int count) { emu_jitter(); emu_block->get_named(id, count).arrive_and_wait(); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 [[noreturn]] inline void __trap() {

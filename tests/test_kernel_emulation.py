@@ -149,3 +149,23 @@ def test_pipelined_kernel_on_cpu_threads(emu, world, grid, algo, pipe_k):
                 step += 1
     finally:
         emu.emu_group_destroy(g)
+
+
+@pytest.mark.parametrize("algo", [2, 5, 6])
+def test_kernels_with_scheduling_jitter(emu, algo, monkeypatch):
+    """Random 0-300 us sleeps at 2 % of all barrier entries (B2D_EMU_JITTER): roles, blocks and ranks drift far apart;
+    six consecutive launches on alternating halves must still match the oracle bit for bit."""
+    monkeypatch.setenv("B2D_EMU_JITTER", "20")
+    world, grid = 4, 2
+    g = emu.emu_group_create(world, 8 << 20)
+    try:
+        for step in range(6):
+            n = 30011 + 997 * step
+            per_rank = inputs(world, n, 900 + step)
+            bufs = [t.numpy().copy() for t in per_rank]
+            assert emu.emu_allreduce(g, algo, 1, ptrs(bufs), n, 0.25, grid, step & 1, 0, 1) == 0
+            want = ddp_oracle.allreduce_bf16_wire(per_rank).numpy()
+            for r in range(world):
+                assert same_bits(bufs[r], want), (algo, step, r)
+    finally:
+        emu.emu_group_destroy(g)
