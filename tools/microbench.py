@@ -180,5 +180,27 @@ def sweep():
     dist.destroy_process_group()
 
 
+def ncu_target():
+    """A tiny multi-rank workload meant to run with EVERY rank under its own ncu (single-pass metrics, no kernel
+    replay): a few allreduce calls of one size.  See tools/gpu_runs/ncu_multirank.sh."""
+    import torch.distributed as dist
+    from ray_lightning_b200.comm import Communicator
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")          # control plane only; keeps NCCL kernels out of the capture
+    wire_bytes = int(os.environ.get("B2D_NCU_WIRE_BYTES", str(16 << 20)))
+    algo = os.environ.get("B2D_NCU_ALGO", "two_shot")
+    comm = Communicator(rank, world, local, 1 << 30, mem="vmm", timeout_ms=5000, nvls="auto",
+                        max_ctas=int(os.environ.get("B2D_MAX_CTAS", "64")))
+    buf = torch.randn(wire_bytes // 2, device="cuda") * 0.01
+    for i in range(6):
+        comm.allreduce_(buf, bucket_idx=0, wire="bf16", algo=algo)
+        torch.cuda.synchronize()
+        dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
-    {"k0": k0, "loopback": loopback, "sweep": sweep}[sys.argv[1]]()
+    {"k0": k0, "loopback": loopback, "sweep": sweep, "ncu_target": ncu_target}[sys.argv[1]]()
