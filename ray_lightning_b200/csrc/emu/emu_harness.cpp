@@ -207,6 +207,50 @@ int emu_sharded_step(void* h, int bf16, float** grads, size_t param_off, float**
   return launch_all(world, grid, kThreads, bodies);
 }
 
+// K4 alone (reduce-scatter to owner, fp32 out) and K6 alone (all-gather of a flat arena buffer, with its end barrier)
+int emu_reduce_scatter(void* h, int bf16, float** grads, float** outs, size_t n, const long long* shard_off, float scale,
+                       size_t stage_base, int grid, int parity) {
+  Group* g = static_cast<Group*>(h);
+  const int world = g->world;
+  const size_t half = (n * (bf16 ? 2 : 4) + 255) / 256 * 256;
+  if (stage_base + 2 * half > g->arena_bytes) return -4;
+  std::vector<ShParams> params(world);
+  std::vector<std::function<void()>> bodies(world);
+  for (int r = 0; r < world; ++r) {
+    ShParams P{};
+    P.grads = grads[r]; P.rs_out = outs[r]; P.n = n;
+    for (int i = 0; i <= world; ++i) P.off[i] = shard_off[i];
+    for (int i = world + 1; i <= B2D_MAX_WORLD; ++i) P.off[i] = shard_off[world];
+    P.stage_off = stage_base + (parity & 1) * half; P.scale = scale; P.rank = r; P.world = world;
+    P.do_stage_reduce = 1; P.do_adam = 0; P.do_gather = 0;
+    P.timeout_ns = 60ull * 1000000000ull; P.peers = make_peers(*g);
+    params[r] = P;
+    const ShParams* pp = &params[r];
+    bodies[r] = bf16 ? std::function<void()>([=] { k456_sharded_kernel<0, true>(*pp); })
+                     : std::function<void()>([=] { k456_sharded_kernel<0, false>(*pp); });
+  }
+  return launch_all(world, grid, kThreads, bodies);
+}
+
+int emu_allgather(void* h, size_t buf_off, size_t n, const long long* shard_off, int grid) {
+  Group* g = static_cast<Group*>(h);
+  const int world = g->world;
+  std::vector<ShParams> params(world);
+  std::vector<std::function<void()>> bodies(world);
+  for (int r = 0; r < world; ++r) {
+    ShParams P{};
+    P.params = reinterpret_cast<float*>(g->arena[r] + buf_off); P.param_off = buf_off; P.n = n;
+    for (int i = 0; i <= world; ++i) P.off[i] = shard_off[i];
+    for (int i = world + 1; i <= B2D_MAX_WORLD; ++i) P.off[i] = shard_off[world];
+    P.rank = r; P.world = world; P.do_gather = 1; P.end_barrier = 1;
+    P.timeout_ns = 60ull * 1000000000ull; P.peers = make_peers(*g);
+    params[r] = P;
+    const ShParams* pp = &params[r];
+    bodies[r] = std::function<void()>([=] { k456_sharded_kernel<0, false>(*pp); });
+  }
+  return launch_all(world, grid, kThreads, bodies);
+}
+
 float* emu_arena_ptr(void* h, int rank, size_t off) {
   return reinterpret_cast<float*>(static_cast<Group*>(h)->arena[rank] + off);
 }

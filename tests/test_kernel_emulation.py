@@ -37,6 +37,9 @@ def emu(tmp_path_factory):
                                      ctypes.POINTER(FP), ctypes.c_size_t, ctypes.POINTER(ctypes.c_longlong), ctypes.c_float,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.emu_reduce_scatter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(FP), ctypes.POINTER(FP), ctypes.c_size_t,
+                                       ctypes.POINTER(ctypes.c_longlong), ctypes.c_float, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+    lib.emu_allgather.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
     lib.emu_arena_ptr.restype = FP
     lib.emu_arena_ptr.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]
     return lib
@@ -167,5 +170,47 @@ def test_kernels_with_scheduling_jitter(emu, algo, monkeypatch):
             want = ddp_oracle.allreduce_bf16_wire(per_rank).numpy()
             for r in range(world):
                 assert same_bits(bufs[r], want), (algo, step, r)
+    finally:
+        emu.emu_group_destroy(g)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_reduce_scatter_and_allgather_alone_on_cpu_threads(emu, world):
+    """K4 and K6 as separate launches (the path of optimizers other than Adam): reduce-scatter bit-exact for both
+    wires, then an all-gather of a flat arena buffer whose shards were filled by their owners."""
+    rng = np.random.default_rng(5)
+    numels = [int(x) for x in rng.integers(1, 900, size=7)]
+    owner = ddp_oracle.partition_fairscale(numels, world)
+    _, shard_off, total = ddp_oracle.shard_layout(numels, owner, world)
+    off = (ctypes.c_longlong * (world + 1))(*shard_off)
+    sig = emu.emu_signal_bytes()
+    g = emu.emu_group_create(world, 4 << 20)
+    try:
+        scale = float(np.float32(1.0) / np.float32(world))
+        for step, bf16 in enumerate((0, 1, 0)):
+            per_rank = [torch.randn(total, generator=torch.Generator().manual_seed(31 * step + r)) * 0.1 for r in range(world)]
+            grads = [t.numpy().copy() for t in per_rank]
+            outs = [np.zeros(max(shard_off[r + 1] - shard_off[r], 8), np.float32) for r in range(world)]
+            assert emu.emu_reduce_scatter(g, bf16, ptrs(grads), ptrs(outs), total, off, scale, sig + (1 << 20), 2, step & 1) == 0
+            if bf16:
+                want = None
+                for t in per_rank:
+                    c = ddp_oracle.wire_bf16(t, scale)
+                    want = c if want is None else want + c
+            else:
+                want = ddp_oracle.allreduce_fp32_wire(per_rank, scale)
+            for r in range(world):
+                n_own = shard_off[r + 1] - shard_off[r]
+                assert same_bits(outs[r][:n_own], want[shard_off[r]:shard_off[r + 1]].numpy()), (step, r)
+        full = torch.randn(total, generator=torch.Generator().manual_seed(77)).numpy()
+        views = []
+        for r in range(world):
+            v = np.ctypeslib.as_array(emu.emu_arena_ptr(g, r, sig), shape=(total,))
+            v[:] = 0
+            v[shard_off[r]:shard_off[r + 1]] = full[shard_off[r]:shard_off[r + 1]]
+            views.append(v)
+        assert emu.emu_allgather(g, sig, total, off, 2) == 0
+        for r in range(world):
+            assert same_bits(views[r], full), r
     finally:
         emu.emu_group_destroy(g)
