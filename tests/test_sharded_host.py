@@ -121,8 +121,10 @@ def test_sharded_optimizer_equals_the_plain_optimizer_on_averaged_grads(world, o
               torch.randn(6, 3, generator=torch.Generator().manual_seed(7 + 100 * s + r))) for r in range(world)]
             for s in range(5)]
 
+    models = [make_model() for _ in range(world)]   # built in the main thread: the global RNG is not thread safe
+
     def rank_fn(r):
-        model = make_model()
+        model = models[r]
         comm = FakeComm(net, r)
         shards = FlatShards(model, comm)
         sopt = ShardedOptimizer(mk(model.parameters()), shards, wire="fp32")
