@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define B2D_VERSION 100          /* 0.1.0 */
+#define B2D_VERSION 110          /* 0.1.10 */
 #define B2D_MAX_WORLD 8          /* one NVSwitch domain: 8 x B200 */
 #define B2D_MAX_BLOCKS 296       /* 2 x 148 SMs */
 #define B2D_HANDLE_BYTES 256     /* size of the blob b2d_ctx_export() writes */
@@ -78,11 +78,14 @@ typedef enum b2d_algo {
   B2D_ALGO_AUTO = 0,
   B2D_ALGO_ONE_SHOT = 1,   /* every rank reads every peer's whole staged bucket */
   B2D_ALGO_TWO_SHOT = 2,   /* reduce-scatter of 1/W slices + all-gather, both by peer reads */
-  B2D_ALGO_NVLS = 3,       /* multimem.ld_reduce / multimem.st through the NVSwitch */
+  B2D_ALGO_NVLS = 3,       /* staged exchange, reduce + broadcast inside the NVSwitch
+                              (multimem.ld_reduce / multimem.st); sums in switch order: tolerance contract */
   B2D_ALGO_TWO_SHOT_TMA = 4, /* two-shot with every load a TMA bulk copy into a shared-memory ring (bf16 wire,
                                n % 8 == 0; other shapes fall back to B2D_ALGO_TWO_SHOT) */
-  B2D_ALGO_TWO_SHOT_PIPE = 5, /* EXPERIMENTAL role-decoupled chunk pipeline (world 2/4/8; else falls back) */
-  B2D_ALGO_NVLS_PIPE = 6      /* EXPERIMENTAL the same pipeline with multimem.ld_reduce / multimem.st */
+  B2D_ALGO_STAGED = 5,     /* staged exchange over peer loads/stores: stage | reduce own slice + push | write back
+                              as separate short kernels on three streams, chunk-pipelined; rank-ordered fp32
+                              sums, bit-identical to ONE_SHOT / TWO_SHOT */
+  B2D_ALGO_NVLS_FUSED = 6  /* round-1 single-kernel NVLS two-shot (kept for A/B sweeps) */
 } b2d_algo;
 
 /* b2d_ctx_create flags */
@@ -138,10 +141,13 @@ const char* b2d_last_error(b2d_ctx* ctx);
 
 /* ---- knobs ----------------------------------------------------------------------------- */
 
-int b2d_ctx_set_timeout(b2d_ctx* ctx, unsigned timeout_ms);  /* peer-flag watchdog; default 10000 */
+int b2d_ctx_set_timeout(b2d_ctx* ctx, unsigned timeout_ms);  /* peer-flag watchdog; default 600000 (10 min), 0 = never */
 int b2d_ctx_set_max_ctas(b2d_ctx* ctx, int max_ctas);        /* CTAs per comm kernel; default 64 */
 int b2d_ctx_set_tma_ctas(b2d_ctx* ctx, int ctas);            /* CTAs of the TMA-staged kernel; default 48 */
 int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes); /* AUTO: one-shot at or below */
+int b2d_ctx_set_chunk_bytes(b2d_ctx* ctx, size_t wire_bytes);  /* staged exchange: wire bytes per pipeline chunk; default 32 MiB */
+int b2d_ctx_set_exch_ctas(b2d_ctx* ctx, int ctas);             /* CTAs of the exchange kernel; default 32 */
+int b2d_ctx_set_nvls_auto(b2d_ctx* ctx, int enable);           /* may AUTO pick B2D_ALGO_NVLS when multicast is bound? default 1 */
 
 /* ---- data path ------------------------------------------------------------------------- */
 
@@ -160,6 +166,15 @@ int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes); /* AUTO: on
 int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad_inout, size_t n,
                          int wire, float scale, int algo,
                          void* wait_stream, void* comm_stream);
+
+/* The same call issued phase by phase (bit 0: stage, bit 1: exchange, bit 2: wait + write back; 7 = all, which
+ * is what b2d_allreduce_bucket does).  Only the staged algorithms (B2D_ALGO_STAGED / B2D_ALGO_NVLS, or AUTO
+ * resolving to them) accept a partial mask.  For hosts that drive SEVERAL ranks from one thread (the loopback
+ * tests, smoke() under a serialising profiler): issue phase 1 for every rank, then 2, then 4 — no kernel then
+ * ever waits for a kernel launched after it.  Replaces nothing in the reference (NCCL has no such seam). */
+int b2d_allreduce_bucket_phased(b2d_ctx* ctx, int bucket_idx, float* grad_inout, size_t n,
+                                int wire, float scale, int algo, unsigned phases,
+                                void* wait_stream, void* comm_stream);
 
 /* Hyper-parameters of the partitioned Adam (torch/optim/adam.py:347-547 semantics,
  * non-amsgrad, non-maximize).  `step` is the 1-based step count AFTER increment. */
@@ -211,6 +226,24 @@ int b2d_arena_alloc(b2d_ctx* ctx, size_t bytes, void** dev_ptr, size_t* offset);
 /* Forget every bucket slot and arena allocation (host must have quiesced all ranks). */
 int b2d_arena_reset(b2d_ctx* ctx);
 
+/* ---- torch memory pool over the arena (f-1: zero-copy stage-in) ----------------------- */
+
+/* Replaces: the cudaMalloc behind at::empty() for DDP's flat bucket tensors (reducer.hpp:347-406,
+ * initialize_buckets), reached from ray_lightning/ray_ddp.py:75,112-116 with gradient_as_bucket_view=True.
+ * b2d_pool_alloc / b2d_pool_free have the signature torch.cuda.memory.CUDAPluggableAllocator expects; while a
+ * context is bound (b2d_pool_bind; NULL unbinds) allocations of its device are bump-allocated from its
+ * symmetric arena.  A bucket that lives there is exchanged IN PLACE by the fp32-wire staged algorithms. */
+int b2d_pool_bind(b2d_ctx* ctx);
+void* b2d_pool_alloc(size_t size, int device, void* stream);
+void b2d_pool_free(void* ptr, size_t size, int device, void* stream);
+
+/* ---- link probe ------------------------------------------------------------------------ */
+
+/* Replaces: nothing (measurement aid).  Pull `bytes` from peer `peer`'s arena `iters` times and report GB/s:
+ * mode 0 = cudaMemcpyAsync, mode 1 = a 16-byte-vector peer-read kernel (this library's access pattern).
+ * Synchronises its own private stream only. */
+int b2d_peer_bw(b2d_ctx* ctx, int peer, size_t bytes, int iters, int mode, double* gbps);
+
 /* ---- introspection --------------------------------------------------------------------- */
 
 typedef struct b2d_stats {
@@ -222,6 +255,10 @@ typedef struct b2d_stats {
   int32_t mem_kind;        /* 0 legacy IPC, 1 VMM */
   int32_t mc_bound;        /* 1 when NVLS is usable */
   int32_t last_algo, last_grid, last_block;
+  int32_t pad_;
+  uint64_t exch_launches;  /* exchange kernels (staged algorithms) launched */
+  uint64_t exch_timed;     /* bucket exchanges bracketed by events (B2D_FLAG_TIMING) and resolved */
+  double exch_ms;          /* sum of their device durations (first exchange kernel start .. last end) */
 } b2d_stats;
 
 int b2d_ctx_stats(b2d_ctx* ctx, b2d_stats* out);   /* resolves finished timing events */

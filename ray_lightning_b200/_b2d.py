@@ -15,12 +15,13 @@ MAX_WORLD = 8
 MAX_BLOCKS = 296
 
 WIRE_FP32, WIRE_BF16 = 0, 1
-ALGO_AUTO, ALGO_ONE_SHOT, ALGO_TWO_SHOT, ALGO_NVLS, ALGO_TWO_SHOT_TMA, ALGO_TWO_SHOT_PIPE, ALGO_NVLS_PIPE = 0, 1, 2, 3, 4, 5, 6
+ALGO_AUTO, ALGO_ONE_SHOT, ALGO_TWO_SHOT, ALGO_NVLS, ALGO_TWO_SHOT_TMA, ALGO_STAGED, ALGO_NVLS_FUSED = 0, 1, 2, 3, 4, 5, 6
+PHASE_STAGE, PHASE_EXCHANGE, PHASE_WRITEBACK, PHASE_ALL = 1, 2, 4, 7
 FLAG_MEM_LEGACY_IPC, FLAG_MEM_VMM, FLAG_TIMING = 0x0, 0x1, 0x2
 
 WIRE_NAMES = {"fp32": WIRE_FP32, "bf16": WIRE_BF16}
 ALGO_NAMES = {"auto": ALGO_AUTO, "one_shot": ALGO_ONE_SHOT, "two_shot": ALGO_TWO_SHOT, "nvls": ALGO_NVLS,
-              "two_shot_tma": ALGO_TWO_SHOT_TMA, "two_shot_pipe": ALGO_TWO_SHOT_PIPE, "nvls_pipe": ALGO_NVLS_PIPE}
+              "two_shot_tma": ALGO_TWO_SHOT_TMA, "staged": ALGO_STAGED, "nvls_fused": ALGO_NVLS_FUSED}
 
 # every symbol include/b2d.h declares (checked by tests/test_cabi.py on a GPU-less box)
 EXPORTED_SYMBOLS = [
@@ -30,6 +31,8 @@ EXPORTED_SYMBOLS = [
     "b2d_ctx_set_one_shot_max_bytes", "b2d_allreduce_bucket", "b2d_sharded_step", "b2d_reduce_scatter",
     "b2d_allgather", "b2d_barrier", "b2d_arena_alloc", "b2d_arena_reset", "b2d_ctx_stats",
     "b2d_ctx_reset_stats", "b2d_plan", "b2d_ctx_trace", "b2d_ctx_set_tma_ctas",
+    "b2d_allreduce_bucket_phased", "b2d_ctx_set_chunk_bytes", "b2d_ctx_set_exch_ctas", "b2d_ctx_set_nvls_auto",
+    "b2d_peer_bw", "b2d_pool_bind", "b2d_pool_alloc", "b2d_pool_free",
 ]
 
 
@@ -55,7 +58,8 @@ class Stats(ctypes.Structure):
                 ("arena_used", ctypes.c_uint64), ("world", ctypes.c_int32), ("rank", ctypes.c_int32),
                 ("device", ctypes.c_int32), ("sm_count", ctypes.c_int32), ("mem_kind", ctypes.c_int32),
                 ("mc_bound", ctypes.c_int32), ("last_algo", ctypes.c_int32), ("last_grid", ctypes.c_int32),
-                ("last_block", ctypes.c_int32)]
+                ("last_block", ctypes.c_int32), ("pad_", ctypes.c_int32), ("exch_launches", ctypes.c_uint64),
+                ("exch_timed", ctypes.c_uint64), ("exch_ms", ctypes.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -88,6 +92,12 @@ def _declare(lib):
         "b2d_ctx_set_tma_ctas": [vp, c.c_int],
         "b2d_ctx_set_one_shot_max_bytes": [vp, sz],
         "b2d_allreduce_bucket": [vp, c.c_int, vp, sz, c.c_int, c.c_float, c.c_int, vp, vp],
+        "b2d_allreduce_bucket_phased": [vp, c.c_int, vp, sz, c.c_int, c.c_float, c.c_int, c.c_uint, vp, vp],
+        "b2d_ctx_set_chunk_bytes": [vp, sz],
+        "b2d_ctx_set_exch_ctas": [vp, c.c_int],
+        "b2d_ctx_set_nvls_auto": [vp, c.c_int],
+        "b2d_peer_bw": [vp, c.c_int, sz, c.c_int, c.c_int, c.POINTER(c.c_double)],
+        "b2d_pool_bind": [vp],
         "b2d_sharded_step": [vp, c.c_int, vp, vp, vp, vp, sz, c.POINTER(c.c_int64), c.c_int, c.c_float,
                              c.POINTER(AdamParams), vp, vp],
         "b2d_reduce_scatter": [vp, c.c_int, vp, vp, sz, c.POINTER(c.c_int64), c.c_int, c.c_float, vp, vp],
@@ -104,6 +114,10 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c.c_int
+    lib.b2d_pool_alloc.argtypes = [sz, c.c_int, vp]
+    lib.b2d_pool_alloc.restype = vp
+    lib.b2d_pool_free.argtypes = [vp, sz, c.c_int, vp]
+    lib.b2d_pool_free.restype = None
 
 
 def load(build_if_missing=True):
@@ -226,11 +240,35 @@ class Context:
     def set_one_shot_max_bytes(self, n):
         self._check(self._lib.b2d_ctx_set_one_shot_max_bytes(self._ctx, int(n)))
 
+    def set_chunk_bytes(self, n):
+        self._check(self._lib.b2d_ctx_set_chunk_bytes(self._ctx, int(n)))
+
+    def set_exch_ctas(self, n):
+        self._check(self._lib.b2d_ctx_set_exch_ctas(self._ctx, int(n)))
+
+    def set_nvls_auto(self, enable):
+        self._check(self._lib.b2d_ctx_set_nvls_auto(self._ctx, int(bool(enable))))
+
+    def pool_bind(self, bind=True):
+        """Route torch's pluggable-allocator calls (b2d_pool_alloc) to this context's arena, or unbind."""
+        self._check(self._lib.b2d_pool_bind(self._ctx if bind else None))
+
+    def peer_bw(self, peer, nbytes, iters=10, mode=1):
+        """GB/s this GPU pulls from ``peer``'s arena (mode 0: cudaMemcpyAsync, 1: peer-read kernel)."""
+        v = ctypes.c_double(0.0)
+        self._check(self._lib.b2d_peer_bw(self._ctx, int(peer), int(nbytes), int(iters), int(mode), ctypes.byref(v)))
+        return v.value
+
     # -- data path (raw pointers; tensor-level wrappers live in comm.py)
-    def allreduce_bucket(self, bucket_idx, ptr, n, wire, scale, algo, wait_stream, comm_stream):
-        self._check(self._lib.b2d_allreduce_bucket(
-            self._ctx, int(bucket_idx), ctypes.c_void_p(ptr), int(n), int(wire), float(scale), int(algo),
-            _stream_ptr(wait_stream), _stream_ptr(comm_stream)))
+    def allreduce_bucket(self, bucket_idx, ptr, n, wire, scale, algo, wait_stream, comm_stream, phases=PHASE_ALL):
+        if phases == PHASE_ALL:
+            self._check(self._lib.b2d_allreduce_bucket(
+                self._ctx, int(bucket_idx), ctypes.c_void_p(ptr), int(n), int(wire), float(scale), int(algo),
+                _stream_ptr(wait_stream), _stream_ptr(comm_stream)))
+        else:
+            self._check(self._lib.b2d_allreduce_bucket_phased(
+                self._ctx, int(bucket_idx), ctypes.c_void_p(ptr), int(n), int(wire), float(scale), int(algo),
+                int(phases), _stream_ptr(wait_stream), _stream_ptr(comm_stream)))
 
     def sharded_step(self, slot, grads_ptr, params_ptr, m_ptr, v_ptr, n, shard_off, wire, scale, adam,
                      wait_stream, comm_stream):

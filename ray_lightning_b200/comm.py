@@ -69,6 +69,14 @@ def _check_tensor(t, device_index):
         raise ValueError("expected a contiguous float32 tensor")
 
 
+def _boot_id():
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            return f.read().strip()
+    except OSError:
+        return ""
+
+
 # ---- fd passing for VMM handles (SCM_RIGHTS over abstract unix sockets) -------------------
 def _sock_name(token, rank):
     return "\0b2d-%s-%d" % (token, rank)
@@ -112,13 +120,14 @@ class _Base:
     device_index = 0
 
     def allreduce_(self, buf, bucket_idx=0, wire="bf16", scale=None, algo="auto", wait_stream=None,
-                   comm_stream=None):
+                   comm_stream=None, phases=_b2d.PHASE_ALL):
         """In-place allreduce of one flat fp32 bucket: buf <- sum_r buf_r * scale (see b2d.h)."""
         _check_tensor(buf, self.device_index)
         scale = (1.0 / self.world) if scale is None else scale
         ws = torch.cuda.current_stream(buf.device) if wait_stream is None else wait_stream
         cs = ws if comm_stream is None else comm_stream
-        self.ctx.allreduce_bucket(bucket_idx, buf.data_ptr(), buf.numel(), _wire(wire), scale, _algo(algo), ws, cs)
+        self.ctx.allreduce_bucket(bucket_idx, buf.data_ptr(), buf.numel(), _wire(wire), scale, _algo(algo), ws, cs,
+                                  phases)
         return buf
 
     def sharded_step_(self, grads, params, exp_avg, exp_avg_sq, shard_off, step, lr, betas=(0.9, 0.999),
@@ -173,7 +182,8 @@ class Communicator(_Base):
     """
 
     def __init__(self, rank, world, device_index, arena_bytes, group=None, mem="ipc", timing=False,
-                 nvls="auto", timeout_ms=None, max_ctas=None, one_shot_max_bytes=None):
+                 nvls="auto", timeout_ms=None, max_ctas=None, one_shot_max_bytes=None, chunk_bytes=None,
+                 exch_ctas=None):
         if not torch.cuda.is_available():
             raise _b2d.B2DUnavailableError("CUDA is not available: the B200 gradient-sync path has no CPU fallback")
         self.rank, self.world, self.device_index = rank, world, device_index
@@ -188,8 +198,26 @@ class Communicator(_Base):
             self.ctx.set_max_ctas(max_ctas)
         if one_shot_max_bytes is not None:
             self.ctx.set_one_shot_max_bytes(one_shot_max_bytes)
+        if chunk_bytes is not None:
+            self.ctx.set_chunk_bytes(chunk_bytes)
+        if exch_ctas is not None:
+            self.ctx.set_exch_ctas(exch_ctas)
         if world > 1:
+            self._check_single_box()
             self._connect(nvls)
+
+    def _check_single_box(self):
+        """The peer mapping is CUDA IPC / VMM fds inside ONE NVSwitch box: say so early (the reference's NCCL
+        path would go multi-node; this one cannot)."""
+        if self.world > _b2d.MAX_WORLD:
+            raise RuntimeError("libb2d drives one NVSwitch domain of at most %d GPUs; got world size %d"
+                               % (_b2d.MAX_WORLD, self.world))
+        if dist.is_initialized():
+            hosts = [None] * self.world
+            dist.all_gather_object(hosts, (socket.gethostname(), _boot_id()), group=self.group)
+            if len(set(hosts)) != 1:
+                raise RuntimeError("libb2d workers must share one host (got %s): multi-node is out of scope"
+                                   % sorted(set(h for h, _ in hosts)))
 
     def _connect(self, nvls):
         if not dist.is_initialized():
@@ -272,19 +300,23 @@ class _LoopRank(_Base):
 
 
 class LoopbackGroup:
-    """``world`` ranks in this process, all on ``device_index``; rank r launches on its own stream.
+    """``world`` ranks in this process; rank r launches on its own stream.  By default all on ``device_index``
+    (the whole inter-rank protocol on ONE GPU); ``devices=[...]`` spreads them over several GPUs of the box, and
+    with ``mem="vmm"`` + ``nvls=True`` binds an NVLS multicast object over them (needs distinct devices).
 
-    Co-residency: W ranks x grid CTAs x 512 threads must fit the device at once (the kernels
-    spin on each other), so the per-kernel CTA budget is 128 // W."""
+    Co-residency: the single-kernel algorithms (one_shot / two_shot) spin on each other, so W ranks x grid CTAs
+    x 512 threads must fit the device at once: their per-kernel CTA budget is 128 // W.  The staged algorithms
+    never wait for a later launch when their phases are issued phase-major, which is what ``allreduce_`` does."""
 
     def __init__(self, world, device_index=0, arena_bytes=64 << 20, timing=False, timeout_ms=5000,
-                 max_ctas=None, devices=None):
+                 max_ctas=None, devices=None, mem="ipc", nvls=False):
         if not torch.cuda.is_available():
             raise _b2d.B2DUnavailableError("CUDA is not available")
         self.world = world
         devices = [device_index] * world if devices is None else list(devices)
-        flags = FLAG_TIMING if timing else 0
+        flags = (FLAG_TIMING if timing else 0) | (FLAG_MEM_VMM if mem == "vmm" else 0)
         self.ranks = []
+        self.nvls = False
         for r in range(world):
             with torch.cuda.device(devices[r]):
                 ctx = _b2d.Context(r, world, devices[r], arena_bytes, flags)
@@ -298,12 +330,28 @@ class LoopbackGroup:
                 if p != rk.rank:
                     rk.ctx.import_handle(p, blobs[p])
             rk.ctx.finalize()
+        if nvls:
+            if mem != "vmm" or len(set(devices)) != world:
+                raise ValueError("NVLS needs mem='vmm' and one distinct device per rank")
+            fd = self.ranks[0].ctx.mc_create()
+            try:
+                for rk in self.ranks:
+                    rk.ctx.mc_join(fd)
+                for rk in self.ranks:
+                    rk.ctx.mc_bind()
+            finally:
+                os.close(fd)
+            self.nvls = True
 
     def allreduce_(self, bufs, bucket_idx=0, wire="bf16", scale=None, algo="auto"):
         """bufs[r] is rank r's bucket; all are reduced in place. Asynchronous."""
-        for rk, b in zip(self.ranks, bufs):
-            rk.allreduce_(b, bucket_idx, wire, scale, algo,
-                          wait_stream=torch.cuda.current_stream(b.device), comm_stream=rk.stream)
+        a = self.ranks[0].ctx.plan(bufs[0].numel(), _wire(wire), _algo(algo))[0]
+        phase_sets = ((_b2d.PHASE_STAGE, _b2d.PHASE_EXCHANGE, _b2d.PHASE_WRITEBACK)
+                      if a in (_b2d.ALGO_STAGED, _b2d.ALGO_NVLS) and self.world > 1 else (_b2d.PHASE_ALL,))
+        for ph in phase_sets:      # phase-major: no kernel ever waits for one launched after it
+            for rk, b in zip(self.ranks, bufs):
+                rk.allreduce_(b, bucket_idx, wire, scale, algo,
+                              wait_stream=torch.cuda.current_stream(b.device), comm_stream=rk.stream, phases=ph)
         return bufs
 
     def sharded_step_(self, grads, params, exp_avg, exp_avg_sq, shard_off, **kw):

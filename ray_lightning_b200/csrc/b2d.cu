@@ -18,7 +18,7 @@
 
 #include "b2d_kernels.cuh"
 #include "b2d_tma.cuh"
-#include "b2d_pipe.cuh"
+#include "b2d_staged.cuh"
 
 using namespace b2d;
 
@@ -41,7 +41,8 @@ struct HandleBlob {
   int32_t fd;            // POSIX fd of the VMM allocation *in the importing process* (patched)
   int32_t pad;
   cudaIpcMemHandle_t ipc;
-  unsigned char reserved[B2D_HANDLE_BYTES - 64 - sizeof(cudaIpcMemHandle_t)];
+  uint64_t proc_nonce;   // random per process: equal pids in different pid namespaces / hosts must not look local
+  unsigned char reserved[B2D_HANDLE_BYTES - 72 - sizeof(cudaIpcMemHandle_t)];
 };
 static_assert(sizeof(HandleBlob) == B2D_HANDLE_BYTES, "handle blob size is part of the ABI");
 
@@ -125,7 +126,23 @@ struct Slot {
   size_t n = 0;
   int wire = -1, algo = -1, grid = 0;
   unsigned parity = 0;
+  // staged exchange: the op whose phases are being issued (b2d_allreduce_bucket_phased) and, per half, the
+  // event after which the half may be staged into again (its last write-back has finished)
+  uint32_t op_epoch0 = 0;
+  size_t op_stage_off = 0;
+  cudaEvent_t reuse_ev[2] = {nullptr, nullptr};
 };
+
+uint64_t process_nonce() {
+  static const uint64_t nonce = [] {
+    uint64_t v = 0;
+    FILE* f = fopen("/dev/urandom", "rb");
+    if (f != nullptr) { if (fread(&v, sizeof(v), 1, f) != 1) v = 0; fclose(f); }
+    if (v == 0) v = (static_cast<uint64_t>(getpid()) << 32) ^ static_cast<uint64_t>(reinterpret_cast<uintptr_t>(&v));
+    return v;
+  }();
+  return nonce;
+}
 
 enum PeerMap { kMapNone = 0, kMapSelf, kMapDirect, kMapLegacyIpc, kMapVmm };
 
@@ -176,6 +193,20 @@ struct b2d_ctx {
   std::map<int, Slot> slots;
   size_t slot_top = 0;     // slots grow up from just above the signal pad
   size_t user_bottom = 0;  // user allocations grow down from the end of the arena
+  std::map<size_t, size_t> slot_free;   // offset -> bytes: regions given back by re-laid-out slots (first fit)
+
+  // staged exchange (b2d_staged.cuh): three internal streams, a ring of ordering events, the chunk epoch
+  cudaStream_t s_stage = nullptr, s_xfer = nullptr, s_unstage = nullptr;
+  std::vector<cudaEvent_t> ev_ring;
+  size_t ev_ring_idx = 0;
+  cudaEvent_t last_unstage_ev = nullptr;
+  uint32_t epoch = 0;
+  size_t chunk_bytes = 32u << 20;        // wire bytes per pipeline chunk
+  int exch_ctas = 32;                    // CTAs of the exchange kernel (the only one that waits for peers)
+  int nvls_auto = 1;                     // AUTO may pick the in-switch reduction when a multicast object is bound
+  uint64_t exch_launches = 0, exch_timed = 0;
+  double exch_ms = 0.0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> exch_pending;
 
   unsigned long long* trace_dev = nullptr;   // debug: per-block phase stamps of the LAST allreduce launch
   int trace_grid = 0;
@@ -186,9 +217,10 @@ struct b2d_ctx {
   int max_ctas = 64;
   int tma_ctas = 48;        // CTAs of the TMA-staged kernel (b2d_ctx_set_max_ctas caps it too)
   int tma_ctas_user = 0;
-  int pipe_runs_per_chunk = 4;   // K2P: runs of 128 packs per chunk and block
-  size_t one_shot_max_bytes = 1024 * 1024;
-  unsigned timeout_ms = 10000;
+  size_t one_shot_max_bytes = 512 * 1024;
+  // peer watchdog: minutes, like a process-group timeout — a rank that is late because of a slow data loader,
+  // rank-0 logging or a debugger pause must not poison the CUDA context (b2d_ctx_set_timeout; 0 = never trap)
+  unsigned timeout_ms = 600000;
   int last_algo = 0, last_grid = 0, last_block = 0;
 
   std::string err;
@@ -340,18 +372,19 @@ int launch_barrier(b2d_ctx* ctx, cudaStream_t stream) {
   return B2D_OK;
 }
 
+bool is_staged(int algo) { return algo == B2D_ALGO_STAGED || algo == B2D_ALGO_NVLS; }
+
 int pick_algo(b2d_ctx* ctx, size_t n, int wire, int algo) {
   if (ctx->world == 1) return B2D_ALGO_ONE_SHOT;
   if (algo == B2D_ALGO_TWO_SHOT_TMA && (wire != B2D_WIRE_BF16 || n % 8 != 0)) return B2D_ALGO_TWO_SHOT;
-  if ((algo == B2D_ALGO_TWO_SHOT_PIPE || algo == B2D_ALGO_NVLS_PIPE) && ctx->world != 2 && ctx->world != 4 && ctx->world != 8)
-    return algo == B2D_ALGO_NVLS_PIPE ? B2D_ALGO_NVLS : B2D_ALGO_TWO_SHOT;
   if (algo != B2D_ALGO_AUTO) return algo;
   const size_t wire_bytes = n * (wire == B2D_WIRE_BF16 ? 2 : 4);
-  // at world 2 one-shot moves exactly the two-shot's bytes with one barrier less
-  if (ctx->world == 2 || wire_bytes <= ctx->one_shot_max_bytes) return B2D_ALGO_ONE_SHOT;
-  // NVLS is opt-in (B2D_ALGO_NVLS): the switch sums in its own order, so its results are not the
-  // bit-exact rank-ordered sums of the P2P kernels, and it measured within ~10% of them (profiles/).
-  return B2D_ALGO_TWO_SHOT;
+  // small buckets: one kernel, one barrier, every rank reads everything
+  if (wire_bytes <= ctx->one_shot_max_bytes) return B2D_ALGO_ONE_SHOT;
+  // everything else goes through the staged exchange; the in-switch reduction pays from 4 ranks up
+  // ((1 + 1/W) N w bytes per direction instead of 2 (W-1)/W N w; equal at W = 2)
+  if (ctx->mc_bound && ctx->nvls_auto && ctx->world >= 4) return B2D_ALGO_NVLS;
+  return B2D_ALGO_STAGED;
 }
 
 // macro-tile size (packs) of the TMA kernel for a given grid: spread the slice over the grid, 8..4096
@@ -363,15 +396,37 @@ int tma_mt(size_t slice, int grid) {
   return static_cast<int>(mt);
 }
 
+// packs per pipeline chunk of the staged exchange: a multiple of the world size, at least one CTA's worth
+size_t staged_chunk_packs(const b2d_ctx* ctx) {
+  size_t cp = ctx->chunk_bytes / 16;
+  const size_t unit = static_cast<size_t>(ctx->world) * 1024;
+  cp = cp / unit * unit;
+  return cp < unit ? unit : cp;
+}
+
+int exch_grid(const b2d_ctx* ctx, size_t chunk_packs, int algo) {
+  const size_t slice = (chunk_packs + ctx->world - 1) / ctx->world;
+  const size_t per_thread = algo == B2D_ALGO_NVLS ? 8 : (ctx->world <= 8 && kMaxLoadsInFlight / ctx->world > 1 ? kMaxLoadsInFlight / ctx->world : 1);
+  size_t grid = (slice + kExThreads * per_thread - 1) / (kExThreads * per_thread);
+  if (grid < 1) grid = 1;
+  if (grid > static_cast<size_t>(ctx->exch_ctas)) grid = ctx->exch_ctas;
+  return static_cast<int>(grid);
+}
+
+int stream_grid(const b2d_ctx* ctx, size_t packs) {   // S / U: plain streaming kernels, 8 packs per thread
+  size_t grid = (packs + kStThreads * 8 - 1) / (kStThreads * 8);
+  if (grid < 1) grid = 1;
+  const size_t cap = static_cast<size_t>(ctx->sm_count) * 4;
+  if (grid > cap) grid = cap;
+  return static_cast<int>(grid);
+}
+
 int pick_grid(b2d_ctx* ctx, size_t n, int wire, int algo) {
   const size_t epp = wire == B2D_WIRE_BF16 ? 8 : 4;
   const size_t npacks = (n + epp - 1) / epp;
-  if (algo == B2D_ALGO_TWO_SHOT_PIPE || algo == B2D_ALGO_NVLS_PIPE) {
-    const size_t slice = (npacks + ctx->world - 1) / ctx->world;
-    size_t grid = (slice + kPipeRun - 1) / kPipeRun;   // at least one run per block
-    if (grid < 1) grid = 1;
-    if (grid > static_cast<size_t>(ctx->max_ctas)) grid = ctx->max_ctas;
-    return static_cast<int>(grid);
+  if (is_staged(algo)) {
+    const size_t cp = staged_chunk_packs(ctx);
+    return exch_grid(ctx, npacks < cp ? npacks : cp, algo);
   }
   if (algo == B2D_ALGO_TWO_SHOT_TMA) {
     const size_t slice = (npacks + ctx->world - 1) / ctx->world;
@@ -388,32 +443,98 @@ int pick_grid(b2d_ctx* ctx, size_t n, int wire, int algo) {
   return static_cast<int>(grid);
 }
 
+// ---- ordering events of the staged exchange ----------------------------------------------------------------
+cudaEvent_t next_event(b2d_ctx* ctx) {
+  if (ctx->ev_ring.empty()) {
+    ctx->ev_ring.resize(1024, nullptr);
+    for (auto& e : ctx->ev_ring)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); e = nullptr; }
+  }
+  return ctx->ev_ring[ctx->ev_ring_idx++ % ctx->ev_ring.size()];
+}
+
+int ensure_streams(b2d_ctx* ctx) {
+  if (ctx->s_stage != nullptr) return B2D_OK;
+  int lo = 0, hi = 0;   // "greatest" priority is the numerically lowest
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { cudaGetLastError(); lo = hi = 0; }
+  B2D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_stage, cudaStreamNonBlocking, hi));
+  B2D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_xfer, cudaStreamNonBlocking, hi));
+  B2D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_unstage, cudaStreamNonBlocking, hi));
+  return B2D_OK;
+}
+
+// first-fit region allocator for bucket slots (identical call sequence on every rank => identical offsets)
+bool slot_region_alloc(b2d_ctx* ctx, size_t bytes, size_t* off) {
+  for (auto it = ctx->slot_free.begin(); it != ctx->slot_free.end(); ++it) {
+    if (it->second >= bytes) {
+      *off = it->first;
+      const size_t rest = it->second - bytes;
+      const size_t rest_off = it->first + bytes;
+      ctx->slot_free.erase(it);
+      if (rest > 0) ctx->slot_free[rest_off] = rest;
+      return true;
+    }
+  }
+  if (ctx->slot_top + bytes > ctx->user_bottom) return false;
+  *off = ctx->slot_top;
+  ctx->slot_top += bytes;
+  return true;
+}
+
+void slot_region_free(b2d_ctx* ctx, size_t off, size_t bytes) {
+  if (bytes == 0) return;
+  ctx->slot_free[off] = bytes;
+  auto it = ctx->slot_free.find(off);
+  auto nx = std::next(it);
+  if (nx != ctx->slot_free.end() && it->first + it->second == nx->first) { it->second += nx->second; ctx->slot_free.erase(nx); }
+  if (it != ctx->slot_free.begin()) {
+    auto pv = std::prev(it);
+    if (pv->first + pv->second == it->first) { pv->second += it->second; ctx->slot_free.erase(it); it = pv; }
+  }
+  if (it->first + it->second == ctx->slot_top) { ctx->slot_top = it->first; ctx->slot_free.erase(it); }
+}
+
 // Arena slot of a bucket: two halves used alternately, so that a rank may start staging
 // step k+1 while a slow peer still reads step k's payload.
 int get_slot(b2d_ctx* ctx, int key, size_t half_bytes, size_t n, int wire, int algo, int grid,
-             cudaStream_t stream, size_t* stage_off) {
+             cudaStream_t stream, size_t* stage_off, Slot** slot_out = nullptr, int* half_out = nullptr) {
   half_bytes = round_up(half_bytes, kAlign);
   Slot& s = ctx->slots[key];
   const bool same = s.half >= half_bytes && s.n == n && s.wire == wire && s.algo == algo && s.grid == grid;
   if (!same) {
     if (s.half != 0) {
-      // geometry changed (DDP rebuilt its buckets, reducer.hpp:125-151): peers may still read
-      // the old layout of this region — meet them before anything is re-mapped
+      // geometry changed (DDP rebuilt its buckets, reducer.hpp:125-151): peers may still read the old layout
+      // of this region — drain the own staged pipeline into `stream`, then meet every peer, before anything
+      // is re-mapped; the staging stream continues behind that barrier
+      if (ctx->last_unstage_ev != nullptr) B2D_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->last_unstage_ev, 0));
       int rc = launch_barrier(ctx, stream);
       if (rc != B2D_OK) return rc;
+      if (ctx->s_stage != nullptr) {
+        cudaEvent_t e = next_event(ctx);
+        B2D_CUDA(ctx, cudaEventRecord(e, stream));
+        B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_stage, e, 0));
+        B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_xfer, e, 0));
+      }
     }
     if (s.half < half_bytes) {
-      if (ctx->slot_top + 2 * half_bytes > ctx->user_bottom)
+      const size_t old_off = s.off, old_bytes = 2 * s.half;
+      slot_region_free(ctx, old_off, old_bytes);   // behind the barrier above
+      size_t off = 0;
+      if (!slot_region_alloc(ctx, 2 * half_bytes, &off)) {
+        s.half = 0; s.off = 0; s.n = 0;
         return fail(ctx, B2D_ERR_NOMEM,
                     "symmetric arena exhausted: slot %d needs 2 x %zu bytes, %zu free of %zu", key,
                     half_bytes, ctx->user_bottom - ctx->slot_top, ctx->arena_bytes);
-      s.off = ctx->slot_top;
+      }
+      s.off = off;
       s.half = half_bytes;
-      ctx->slot_top += 2 * half_bytes;
+      s.reuse_ev[0] = s.reuse_ev[1] = nullptr;
     }
     s.n = n; s.wire = wire; s.algo = algo; s.grid = grid;
   }
   *stage_off = s.off + (s.parity & 1u) * s.half;
+  if (slot_out != nullptr) *slot_out = &s;
+  if (half_out != nullptr) *half_out = static_cast<int>(s.parity & 1u);
   s.parity ^= 1u;
   return B2D_OK;
 }
@@ -466,11 +587,13 @@ void preload_world() {
   preload_one(k456_sharded_kernel<W, false>);
 }
 template <int W>
-void preload_pipe() {
-  preload_one(k2p_two_shot_pipe_kernel<W, true, false>);
-  preload_one(k2p_two_shot_pipe_kernel<W, true, true>);
-  preload_one(k2p_two_shot_pipe_kernel<W, false, false>);
-  preload_one(k2p_two_shot_pipe_kernel<W, false, true>);
+void preload_staged() {
+  preload_one(exch_kernel<W, true, false, false>);
+  preload_one(exch_kernel<W, true, true, false>);
+  preload_one(exch_kernel<W, false, false, false>);
+  preload_one(exch_kernel<W, false, true, false>);
+  preload_one(exch_kernel<W, false, false, true>);
+  preload_one(exch_kernel<W, false, true, true>);
 }
 template <int W>
 void tma_attr() {
@@ -479,7 +602,10 @@ void tma_attr() {
 }
 void preload_kernels() {
   tma_attr<0>(); tma_attr<2>(); tma_attr<4>(); tma_attr<8>();
-  preload_pipe<2>(); preload_pipe<4>(); preload_pipe<8>();
+  preload_staged<0>(); preload_staged<2>(); preload_staged<4>(); preload_staged<8>();
+  preload_one(stage_kernel<true>); preload_one(stage_kernel<false>);
+  preload_one(unstage_kernel<true>); preload_one(unstage_kernel<false>);
+  preload_one(arrive_kernel); preload_one(wait_published_kernel); preload_one(peer_read_kernel);
   preload_one(k0_cast_scale_kernel<true>);
   preload_one(k0_cast_scale_kernel<false>);
   preload_one(barrier_kernel);
@@ -487,6 +613,185 @@ void preload_kernels() {
   preload_world<2>();
   preload_world<4>();
   preload_world<8>();
+}
+
+template <bool BF16, bool NVLS, bool INPLACE>
+void launch_exch_w(const ExParams& P, int world, int grid, cudaStream_t st) {
+  switch (world) {
+    case 2: exch_kernel<2, BF16, NVLS, INPLACE><<<grid, kExThreads, 0, st>>>(P); break;
+    case 4: exch_kernel<4, BF16, NVLS, INPLACE><<<grid, kExThreads, 0, st>>>(P); break;
+    case 8: exch_kernel<8, BF16, NVLS, INPLACE><<<grid, kExThreads, 0, st>>>(P); break;
+    default: exch_kernel<0, BF16, NVLS, INPLACE><<<grid, kExThreads, 0, st>>>(P); break;
+  }
+}
+void launch_exch(const ExParams& P, int world, int grid, bool bf16, bool nvls, bool inplace, cudaStream_t st) {
+  if (inplace) {
+    if (nvls) launch_exch_w<false, true, true>(P, world, grid, st); else launch_exch_w<false, false, true>(P, world, grid, st);
+  } else if (bf16) {
+    if (nvls) launch_exch_w<true, true, false>(P, world, grid, st); else launch_exch_w<true, false, false>(P, world, grid, st);
+  } else {
+    if (nvls) launch_exch_w<false, true, false>(P, world, grid, st); else launch_exch_w<false, false, false>(P, world, grid, st);
+  }
+}
+
+void resolve_exch_timing(b2d_ctx* ctx, bool block) {
+  size_t keep = 0;
+  for (size_t i = 0; i < ctx->exch_pending.size(); ++i) {
+    auto& pr = ctx->exch_pending[i];
+    cudaError_t q = block ? cudaEventSynchronize(pr.second) : cudaEventQuery(pr.second);
+    if (q == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { ctx->exch_ms += ms; ctx->exch_timed += 1; }
+      else cudaGetLastError();
+      ctx->ev_free.push_back(pr);
+    } else {
+      cudaGetLastError();
+      ctx->exch_pending[keep++] = pr;
+    }
+  }
+  ctx->exch_pending.resize(keep);
+}
+
+bool take_timing_pair(b2d_ctx* ctx, std::pair<cudaEvent_t, cudaEvent_t>* out) {
+  if (ctx->ev_free.empty() && ctx->ev_pending.size() + ctx->exch_pending.size() >= 8192) { resolve_timing(ctx, false); resolve_exch_timing(ctx, false); }
+  if (ctx->ev_free.empty()) {
+    if (ctx->ev_pending.size() + ctx->exch_pending.size() >= 8192) return false;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaEventCreate(&b) != cudaSuccess) { cudaGetLastError(); cudaEventDestroy(a); return false; }
+    ctx->ev_free.emplace_back(a, b);
+  }
+  *out = ctx->ev_free.back();
+  ctx->ev_free.pop_back();
+  return true;
+}
+
+// The staged exchange of one bucket (b2d_staged.cuh): S on s_stage, X on s_xfer, W+U on s_unstage, chunk by
+// chunk; `comm` only receives the final join.  `phases` (bit 0 S, bit 1 X, bit 2 W+U) lets single-process
+// multi-rank drivers (loopback tests, smoke under ncu) issue the phases of ALL ranks in phase-major order.
+int launch_staged(b2d_ctx* ctx, int key, float* grad, size_t n, int wire, float scale, int algo, unsigned phases,
+                  cudaStream_t wait_s, cudaStream_t comm) {
+  int rc = ensure_streams(ctx);
+  if (rc != B2D_OK) return rc;
+  const bool bf16 = wire == B2D_WIRE_BF16, nvls = algo == B2D_ALGO_NVLS;
+  const size_t epp = bf16 ? 8 : 4;
+  const size_t npacks = (n + epp - 1) / epp;
+  const unsigned char* g8 = reinterpret_cast<const unsigned char*>(grad);
+  const bool inplace = !bf16 && g8 >= ctx->arena + kSignalBytes && g8 + npacks * 16 <= ctx->arena + ctx->arena_bytes;
+  const size_t cp = staged_chunk_packs(ctx);
+  const int nchunks = static_cast<int>((npacks + cp - 1) / cp);
+
+  Slot* slot = nullptr;
+  int half = 0;
+  size_t stage_off = 0;
+  if (inplace) {
+    slot = &ctx->slots[key];          // bookkeeping only (epoch of the op in flight); owns no arena bytes
+    stage_off = static_cast<size_t>(g8 - ctx->arena);
+    if (phases & 1u) slot->op_stage_off = stage_off;
+  } else if (phases & 1u) {
+    rc = get_slot(ctx, key, npacks * 16, n, wire, algo, 0, comm, &stage_off, &slot, &half);
+    if (rc != B2D_OK) return rc;
+    slot->op_stage_off = stage_off;
+  } else {
+    auto it = ctx->slots.find(key);
+    if (it == ctx->slots.end() || it->second.op_epoch0 == 0) return fail(ctx, B2D_ERR_STATE, "phase issued before phase 0 of bucket %d", key);
+    slot = &it->second;
+    stage_off = slot->op_stage_off;
+    half = static_cast<int>((slot->parity ^ 1u) & 1u);
+  }
+  if (phases & 1u) {
+    slot->op_epoch0 = ctx->epoch + 1u;
+    ctx->epoch += static_cast<uint32_t>(nchunks);
+  }
+  const uint32_t epoch0 = slot->op_epoch0;
+  if (epoch0 == 0) return fail(ctx, B2D_ERR_STATE, "phase issued before phase 0 of bucket %d", key);
+
+  StParams SP{};
+  SP.scale = scale; SP.rank = ctx->rank; SP.world = ctx->world; SP.peers = ctx->peers;
+  ExParams XP{};
+  XP.scale = scale; XP.rank = ctx->rank; XP.world = ctx->world; XP.peers = ctx->peers;
+  XP.timeout_ns = static_cast<unsigned long long>(ctx->timeout_ms) * 1000000ull; XP.diag = ctx->diag_dev;
+
+  std::vector<cudaEvent_t> ev_s(nchunks, nullptr), ev_x(nchunks, nullptr);
+  if (phases & 1u) {
+    cudaEvent_t e = ctx->wait_ev[ctx->wait_ev_idx++ % 8];
+    B2D_CUDA(ctx, cudaEventRecord(e, wait_s));
+    B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_stage, e, 0));
+    if (!inplace && slot->reuse_ev[half] != nullptr) B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_stage, slot->reuse_ev[half], 0));
+    if (inplace) {
+      SP.epoch = epoch0 + static_cast<uint32_t>(nchunks) - 1u;   // the whole bucket is ready at once
+      arrive_kernel<<<1, 32, 0, ctx->s_stage>>>(SP);
+      ctx->launches += 1;
+      cudaEvent_t es = next_event(ctx);
+      B2D_CUDA(ctx, cudaEventRecord(es, ctx->s_stage));
+      for (int c = 0; c < nchunks; ++c) ev_s[c] = es;
+    } else {
+      for (int c = 0; c < nchunks; ++c) {
+        const size_t p0 = static_cast<size_t>(c) * cp, pc = (npacks - p0 < cp) ? npacks - p0 : cp;
+        SP.grad = grad + p0 * epp;
+        SP.n = (p0 + pc) * epp <= n ? pc * epp : n - p0 * epp;
+        SP.wire = reinterpret_cast<uint4*>(ctx->arena + stage_off) + p0;
+        SP.epoch = epoch0 + static_cast<uint32_t>(c);
+        const int grid = stream_grid(ctx, pc);
+        if (bf16) stage_kernel<true><<<grid, kStThreads, 0, ctx->s_stage>>>(SP); else stage_kernel<false><<<grid, kStThreads, 0, ctx->s_stage>>>(SP);
+        ctx->launches += 1;
+        ev_s[c] = next_event(ctx);
+        B2D_CUDA(ctx, cudaEventRecord(ev_s[c], ctx->s_stage));
+      }
+    }
+  }
+  if (phases & 2u) {
+    std::pair<cudaEvent_t, cudaEvent_t> tp{nullptr, nullptr};
+    const bool timing = (ctx->flags & B2D_FLAG_TIMING) && take_timing_pair(ctx, &tp);
+    for (int c = 0; c < nchunks; ++c) {
+      const size_t p0 = static_cast<size_t>(c) * cp, pc = (npacks - p0 < cp) ? npacks - p0 : cp;
+      if (ev_s[c] != nullptr && (c == 0 || ev_s[c] != ev_s[c - 1])) B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_xfer, ev_s[c], 0));
+      if (timing && c == 0) B2D_CUDA(ctx, cudaEventRecord(tp.first, ctx->s_xfer));
+      XP.wire_off = stage_off + p0 * 16;
+      XP.npacks = pc;
+      XP.n_valid = inplace ? (n - p0 * 4 < pc * 4 ? n - p0 * 4 : pc * 4) : 0;
+      XP.epoch = epoch0 + static_cast<uint32_t>(c);
+      const int grid = exch_grid(ctx, pc, algo);
+      launch_exch(XP, ctx->world, grid, bf16, nvls, inplace, ctx->s_xfer);
+      ctx->launches += 1;
+      ctx->exch_launches += 1;
+      ctx->last_grid = grid;
+      ev_x[c] = next_event(ctx);
+      B2D_CUDA(ctx, cudaEventRecord(ev_x[c], ctx->s_xfer));
+    }
+    if (timing) {
+      B2D_CUDA(ctx, cudaEventRecord(tp.second, ctx->s_xfer));
+      ctx->exch_pending.push_back(tp);
+    }
+  }
+  if (phases & 4u) {
+    for (int c = 0; c < nchunks; ++c) {
+      const size_t p0 = static_cast<size_t>(c) * cp, pc = (npacks - p0 < cp) ? npacks - p0 : cp;
+      if (ev_x[c] != nullptr) B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_unstage, ev_x[c], 0));
+      XP.epoch = epoch0 + static_cast<uint32_t>(c);
+      wait_published_kernel<<<1, 32, 0, ctx->s_unstage>>>(XP);
+      ctx->launches += 1;
+      if (!inplace) {
+        SP.grad = grad + p0 * epp;
+        SP.n = (p0 + pc) * epp <= n ? pc * epp : n - p0 * epp;
+        SP.wire = reinterpret_cast<uint4*>(ctx->arena + stage_off) + p0;
+        SP.epoch = epoch0 + static_cast<uint32_t>(c);
+        const int grid = stream_grid(ctx, pc);
+        if (bf16) unstage_kernel<true><<<grid, kStThreads, 0, ctx->s_unstage>>>(SP); else unstage_kernel<false><<<grid, kStThreads, 0, ctx->s_unstage>>>(SP);
+        ctx->launches += 1;
+      }
+    }
+    cudaEvent_t ed = next_event(ctx);
+    B2D_CUDA(ctx, cudaEventRecord(ed, ctx->s_unstage));
+    B2D_CUDA(ctx, cudaStreamWaitEvent(comm, ed, 0));
+    ctx->last_unstage_ev = ed;
+    if (!inplace) slot->reuse_ev[half] = ed;
+    slot->op_epoch0 = 0;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  ctx->last_algo = algo; ctx->last_block = kExThreads;
+  return B2D_OK;
 }
 
 int check_ready(b2d_ctx* ctx) {
@@ -615,6 +920,7 @@ int b2d_ctx_export(b2d_ctx* ctx, void* handle_buf, size_t* len) {
   b.magic = kMagic; b.version = B2D_VERSION;
   b.rank = ctx->rank; b.world = ctx->world; b.device = ctx->device; b.mem_kind = ctx->mem_kind;
   b.pid = static_cast<int64_t>(getpid());
+  b.proc_nonce = process_nonce();
   b.arena_bytes = ctx->arena_bytes;
   b.arena_ptr = reinterpret_cast<uint64_t>(ctx->arena);
   b.vmm_handle = static_cast<uint64_t>(ctx->vmm_handle);
@@ -658,7 +964,7 @@ int b2d_ctx_import(b2d_ctx* ctx, int peer, const void* handle_buf, size_t len) {
   if (b.mem_kind != ctx->mem_kind) return fail(ctx, B2D_ERR_INVALID, "peer memory kind differs");
   DeviceGuard guard(ctx->device);
   unsigned char* mapped = nullptr;
-  if (b.pid == static_cast<int64_t>(getpid())) {
+  if (b.pid == static_cast<int64_t>(getpid()) && b.proc_nonce == process_nonce()) {
     // another rank of this very process (loopback ranks / single-process multi-GPU)
     mapped = reinterpret_cast<unsigned char*>(b.arena_ptr);
     if (b.device != ctx->device) {
@@ -785,6 +1091,9 @@ int b2d_ctx_destroy(b2d_ctx* ctx) {
     for (auto& pr : ctx->ev_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& e : ctx->wait_ev) if (e != nullptr) cudaEventDestroy(e);
+    for (auto& pr : ctx->exch_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& e : ctx->ev_ring) if (e != nullptr) cudaEventDestroy(e);
+    for (cudaStream_t st : {ctx->s_stage, ctx->s_xfer, ctx->s_unstage}) if (st != nullptr) cudaStreamDestroy(st);
     if (ctx->peers.mc_arena != nullptr) vmm_unmap(ctx->peers.mc_arena, ctx->arena_bytes);
     if (ctx->mc_handle != 0) {
       if (ctx->mc_bound) {
@@ -833,6 +1142,24 @@ int b2d_ctx_set_tma_ctas(b2d_ctx* ctx, int ctas) {
 int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes) {
   if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
   ctx->one_shot_max_bytes = wire_bytes;
+  return B2D_OK;
+}
+
+int b2d_ctx_set_chunk_bytes(b2d_ctx* ctx, size_t wire_bytes) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  if (wire_bytes < (64u << 10)) return fail(ctx, B2D_ERR_INVALID, "chunk must be at least 64 KiB of wire payload");
+  ctx->chunk_bytes = wire_bytes;
+  return B2D_OK;
+}
+int b2d_ctx_set_exch_ctas(b2d_ctx* ctx, int ctas) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  if (ctas < 1 || ctas > B2D_MAX_BLOCKS) return fail(ctx, B2D_ERR_INVALID, "exchange ctas must be in [1, %d]", B2D_MAX_BLOCKS);
+  ctx->exch_ctas = ctas;
+  return B2D_OK;
+}
+int b2d_ctx_set_nvls_auto(b2d_ctx* ctx, int enable) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  ctx->nvls_auto = enable ? 1 : 0;
   return B2D_OK;
 }
 
@@ -893,17 +1220,18 @@ int b2d_plan(b2d_ctx* ctx, size_t n, int wire, int algo, int* algo_out, int* gri
 }
 
 // ---- data path ---------------------------------------------------------------------------
-int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, int wire, float scale,
-                         int algo, void* wait_stream, void* comm_stream) {
+int b2d_allreduce_bucket_phased(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, int wire, float scale,
+                                int algo, unsigned phases, void* wait_stream, void* comm_stream) {
   int rc = check_ready(ctx);
   if (rc != B2D_OK) return rc;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (grad == nullptr && n != 0) return fail(ctx, B2D_ERR_INVALID, "grad is NULL");
   if (reinterpret_cast<uintptr_t>(grad) % 16 != 0) return fail(ctx, B2D_ERR_INVALID, "bucket buffer must be 16-byte aligned");
   if (wire != B2D_WIRE_FP32 && wire != B2D_WIRE_BF16) return fail(ctx, B2D_ERR_INVALID, "bad wire %d", wire);
-  if (algo < B2D_ALGO_AUTO || algo > B2D_ALGO_NVLS_PIPE) return fail(ctx, B2D_ERR_INVALID, "bad algo %d", algo);
-  if (algo == B2D_ALGO_NVLS_PIPE && !ctx->mc_bound && ctx->world > 1) return fail(ctx, B2D_ERR_UNSUPPORTED, "NVLS requested but no multicast object is bound");
-  if (algo == B2D_ALGO_NVLS && !ctx->mc_bound && ctx->world > 1) return fail(ctx, B2D_ERR_UNSUPPORTED, "NVLS requested but no multicast object is bound");
+  if (algo < B2D_ALGO_AUTO || algo > B2D_ALGO_NVLS_FUSED) return fail(ctx, B2D_ERR_INVALID, "bad algo %d", algo);
+  if ((algo == B2D_ALGO_NVLS || algo == B2D_ALGO_NVLS_FUSED) && !ctx->mc_bound && ctx->world > 1)
+    return fail(ctx, B2D_ERR_UNSUPPORTED, "NVLS requested but no multicast object is bound");
+  if (phases == 0 || phases > 7u) return fail(ctx, B2D_ERR_INVALID, "bad phase mask %u", phases);
   if (n == 0) return B2D_OK;  // empty bucket: nothing to exchange, and every rank agrees on that
   DeviceGuard guard(ctx->device);
   if (!guard.ok) return fail(ctx, B2D_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->device);
@@ -911,6 +1239,10 @@ int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, in
 
   int a = 0, grid = 0;
   b2d_plan(ctx, n, wire, algo, &a, &grid, nullptr);
+
+  if (ctx->world > 1 && is_staged(a))
+    return launch_staged(ctx, bucket_idx, grad, n, wire, scale, a, phases, static_cast<cudaStream_t>(wait_stream), comm);
+  if (phases != 7u) return fail(ctx, B2D_ERR_INVALID, "only the staged algorithms can be issued phase by phase");
 
   if (ctx->world == 1) {
     LaunchScope ls{ctx};
@@ -945,26 +1277,9 @@ int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, in
     case B2D_ALGO_TWO_SHOT:
       if (bf) launch_two_shot<true, false>(P, ctx->world, grid, comm); else launch_two_shot<false, false>(P, ctx->world, grid, comm);
       break;
-    case B2D_ALGO_NVLS:
+    case B2D_ALGO_NVLS_FUSED:
       if (bf) launch_two_shot<true, true>(P, ctx->world, grid, comm); else launch_two_shot<false, true>(P, ctx->world, grid, comm);
       break;
-    case B2D_ALGO_TWO_SHOT_PIPE:
-    case B2D_ALGO_NVLS_PIPE: {
-      const int K = ctx->pipe_runs_per_chunk;
-      const bool nv = a == B2D_ALGO_NVLS_PIPE;
-#define B2D_PIPE(WW)                                                                                   \
-      if (bf) { if (nv) k2p_two_shot_pipe_kernel<WW, true, true><<<grid, kThreads, 0, comm>>>(P, K);     \
-                else k2p_two_shot_pipe_kernel<WW, true, false><<<grid, kThreads, 0, comm>>>(P, K); }   \
-      else    { if (nv) k2p_two_shot_pipe_kernel<WW, false, true><<<grid, kThreads, 0, comm>>>(P, K);    \
-                else k2p_two_shot_pipe_kernel<WW, false, false><<<grid, kThreads, 0, comm>>>(P, K); }
-      switch (ctx->world) {
-        case 2: B2D_PIPE(2) break;
-        case 4: B2D_PIPE(4) break;
-        default: B2D_PIPE(8) break;
-      }
-#undef B2D_PIPE
-      break;
-    }
     case B2D_ALGO_TWO_SHOT_TMA: {
       const int mt = tma_mt(slice, grid);
       switch (ctx->world) {
@@ -980,6 +1295,11 @@ int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, in
   }
   ctx->last_algo = a; ctx->last_grid = grid; ctx->last_block = kThreads;
   return ls.end();
+}
+
+int b2d_allreduce_bucket(b2d_ctx* ctx, int bucket_idx, float* grad, size_t n, int wire, float scale,
+                         int algo, void* wait_stream, void* comm_stream) {
+  return b2d_allreduce_bucket_phased(ctx, bucket_idx, grad, n, wire, scale, algo, 7u, wait_stream, comm_stream);
 }
 
 static int sharded_common(b2d_ctx* ctx, int slot, const float* grads, float* params, float* exp_avg,
@@ -1116,9 +1436,77 @@ int b2d_arena_reset(b2d_ctx* ctx) {
   if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->slots.clear();
+  ctx->slot_free.clear();
   ctx->slot_top = kSignalBytes;
   ctx->user_bottom = ctx->arena_bytes;
   return B2D_OK;
+}
+
+// ---- link probe ----------------------------------------------------------------------------
+int b2d_peer_bw(b2d_ctx* ctx, int peer, size_t bytes, int iters, int mode, double* gbps) {
+  int rc = check_ready(ctx);
+  if (rc != B2D_OK) return rc;
+  if (gbps == nullptr || peer < 0 || peer >= ctx->world) return fail(ctx, B2D_ERR_INVALID, "bad peer/gbps");
+  if (iters < 1) iters = 1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  bytes = bytes / 16 * 16;
+  if (bytes == 0 || kSignalBytes + bytes > ctx->arena_bytes) return fail(ctx, B2D_ERR_INVALID, "probe size must fit the arena");
+  void* dst = nullptr;
+  B2D_CUDA(ctx, cudaMalloc(&dst, bytes));
+  const unsigned char* src = ctx->peers.arena[peer] + kSignalBytes;   // content is irrelevant
+  cudaStream_t st = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&a);
+  if (e == cudaSuccess) e = cudaEventCreate(&b);
+  float ms = 0.f;
+  if (e == cudaSuccess) {
+    for (int i = -2; i < iters && e == cudaSuccess; ++i) {
+      if (i == 0) e = cudaEventRecord(a, st);
+      if (e != cudaSuccess) break;
+      if (mode == 0) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
+      else { peer_read_kernel<<<64, kExThreads, 0, st>>>(reinterpret_cast<const uint4*>(src), static_cast<uint4*>(dst), bytes / 16); e = cudaGetLastError(); }
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(b, st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+  }
+  if (a) cudaEventDestroy(a);
+  if (b) cudaEventDestroy(b);
+  if (st) cudaStreamDestroy(st);
+  cudaFree(dst);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, B2D_ERR_CUDA, "link probe failed: %s", cudaGetErrorString(e)); }
+  *gbps = static_cast<double>(bytes) * iters / (static_cast<double>(ms) * 1e6);
+  return B2D_OK;
+}
+
+// ---- the arena as a torch memory pool ---------------------------------------
+// torch.cuda.memory.CUDAPluggableAllocator(libb2d.so, "b2d_pool_alloc", "b2d_pool_free") + torch.cuda.MemPool:
+// whatever torch allocates while that pool is active (DDP's flat bucket tensors, reducer.hpp:347-406) comes
+// out of the bound context's symmetric arena, so peers can reach it and the fp32 exchange runs in place.
+static std::mutex g_pool_mu;
+static b2d_ctx* g_pool_ctx = nullptr;
+
+int b2d_pool_bind(b2d_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pool_ctx = ctx;
+  return B2D_OK;
+}
+
+void* b2d_pool_alloc(size_t size, int device, void* stream) {
+  (void)stream;
+  b2d_ctx* ctx;
+  { std::lock_guard<std::mutex> lk(g_pool_mu); ctx = g_pool_ctx; }
+  if (ctx == nullptr || ctx->device != device) return nullptr;
+  void* p = nullptr;
+  if (b2d_arena_alloc(ctx, size, &p, nullptr) != B2D_OK) return nullptr;
+  return p;
+}
+
+void b2d_pool_free(void* ptr, size_t size, int device, void* stream) {
+  // arena memory lives as long as the context: bump-allocated, given back by b2d_arena_reset / destroy
+  (void)ptr; (void)size; (void)device; (void)stream;
 }
 
 // ---- introspection -----------------------------------------------------------------------
@@ -1128,8 +1516,10 @@ int b2d_ctx_stats(b2d_ctx* ctx, b2d_stats* out) {
   {
     DeviceGuard guard(ctx->device);
     resolve_timing(ctx, false);
+    resolve_exch_timing(ctx, false);
   }
   memset(out, 0, sizeof(*out));
+  out->exch_launches = ctx->exch_launches; out->exch_timed = ctx->exch_timed; out->exch_ms = ctx->exch_ms;
   out->launches = ctx->launches;
   out->timed_launches = ctx->timed_launches;
   out->timed_ms = ctx->timed_ms;
@@ -1147,8 +1537,10 @@ int b2d_ctx_reset_stats(b2d_ctx* ctx) {
   {
     DeviceGuard guard(ctx->device);
     resolve_timing(ctx, true);
+    resolve_exch_timing(ctx, true);
   }
   ctx->launches = 0; ctx->timed_launches = 0; ctx->timed_ms = 0.0;
+  ctx->exch_launches = 0; ctx->exch_timed = 0; ctx->exch_ms = 0.0;
   return B2D_OK;
 }
 

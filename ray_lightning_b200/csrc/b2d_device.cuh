@@ -35,10 +35,11 @@ namespace b2d {
 struct Signal {
   uint32_t flag[2][B2D_MAX_BLOCKS][B2D_MAX_WORLD];
   uint32_t ctr[B2D_MAX_BLOCKS];
-  // K2P (b2d_pipe.cuh): monotone chunk counters, written by rank `src`'s block, and the local base
-  uint32_t cntA[B2D_MAX_BLOCKS][B2D_MAX_WORLD];   // chunks staged so far (cumulative over kernel calls)
-  uint32_t cntB[B2D_MAX_BLOCKS][B2D_MAX_WORLD];   // chunks reduced so far
-  uint32_t pbase[B2D_MAX_BLOCKS];                 // own cumulative chunk count at kernel start (local only)
+  // staged exchange (b2d_staged.cuh): monotone chunk epochs, one word per source rank, written by that
+  // rank's LAST block of the stage / exchange kernel; done_ctr are the local "blocks finished" tickets.
+  uint32_t staged[B2D_MAX_WORLD];
+  uint32_t published[B2D_MAX_WORLD];
+  uint32_t done_ctr[2];
 };
 static_assert(sizeof(Signal) <= 64 * 1024, "signal pad must fit its 64 KiB reservation");
 constexpr size_t kSignalBytes = 64 * 1024;
@@ -97,6 +98,21 @@ __device__ __forceinline__ void multimem_st_v4(void* mc_ptr, const uint4& v) {
   const emu::Multicast& m = emu::multicast();
   const size_t off = static_cast<unsigned char*>(mc_ptr) - m.fake_base;
   for (int r = 0; r < m.world; ++r) emu_st128(m.arena[r] + off, v);
+}
+__device__ __forceinline__ float multimem_ld_reduce_f32(const void* mc_ptr) {
+  const emu::Multicast& m = emu::multicast();
+  const size_t off = static_cast<const unsigned char*>(mc_ptr) - m.fake_base;
+  float acc = 0.f;
+  for (int r = 0; r < m.world; ++r) {
+    const float v = __uint_as_float(emu_ld32(m.arena[r] + off));
+    acc = r == 0 ? v : __fadd_rn(acc, v);
+  }
+  return acc;
+}
+__device__ __forceinline__ void multimem_st_f32(void* mc_ptr, float v) {
+  const emu::Multicast& m = emu::multicast();
+  const size_t off = static_cast<unsigned char*>(mc_ptr) - m.fake_base;
+  for (int r = 0; r < m.world; ++r) emu_st32(m.arena[r] + off, __float_as_uint(v));
 }
 #else
 // Own fp32 gradients: streamed once, keep them out of L1.
@@ -167,6 +183,15 @@ __device__ __forceinline__ void multimem_st_v4(void* mc_ptr, const uint4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_ptr),
                "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+// scalar forms, for the ragged tail of an in-place fp32 bucket
+__device__ __forceinline__ float multimem_ld_reduce_f32(const void* mc_ptr) {
+  float r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(r) : "l"(mc_ptr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_f32(void* mc_ptr, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_ptr), "f"(v) : "memory");
 }
 
 #endif  // B2D_EMU

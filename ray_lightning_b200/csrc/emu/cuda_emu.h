@@ -44,6 +44,7 @@ namespace emu {
 struct Block {
   explicit Block(int nthreads) : n(nthreads), bar0(nthreads) {}
   int n;
+  int scratch = 0;   // stands in for a __shared__ int (b2d_staged.cuh: "was this the last block?")
   std::barrier<> bar0;
   std::mutex mu;
   std::map<int, std::unique_ptr<std::barrier<>>> named;  // id -> barrier(count)
@@ -87,6 +88,7 @@ inline void emu_jitter() {
 inline void __syncthreads() { emu_jitter(); emu_block->bar0.arrive_and_wait(); }
 inline void emu_named_barrier(int id, int count) { emu_jitter(); emu_block->get_named(id, count).arrive_and_wait(); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 [[noreturn]] inline void __trap() {
   std::fprintf(stderr, "emulated kernel trapped (peer timeout)\n");

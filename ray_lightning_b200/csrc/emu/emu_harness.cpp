@@ -10,10 +10,10 @@
 #include <functional>
 #include <vector>
 
+#include <thread>
+
 #include "../b2d_kernels.cuh"
-#ifdef B2D_EMU_WITH_PIPE
-#include "../b2d_pipe.cuh"
-#endif
+#include "../b2d_staged.cuh"
 
 thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 thread_local emu::Block* emu_block = nullptr;
@@ -83,11 +83,29 @@ void run_ar(int algo, const ArParams& P, int pipe_k) {
     case 1: k1_one_shot_kernel<W, BF16>(P); break;
     case 2: k2_two_shot_kernel<W, BF16, false>(P); break;
     case 3: k2_two_shot_kernel<W, BF16, true>(P); break;
-#ifdef B2D_EMU_WITH_PIPE
-    case 5: if constexpr (W == 2 || W == 4 || W == 8) k2p_two_shot_pipe_kernel<W, BF16, false>(P, pipe_k); break;
-    case 6: if constexpr (W == 2 || W == 4 || W == 8) k2p_two_shot_pipe_kernel<W, BF16, true>(P, pipe_k); break;
-#endif
     default: break;
+  }
+}
+
+// one kernel of one rank: grid x block threads, joined before returning (a stream runs these one after another)
+int launch_one(int grid, int block, std::function<void()> body) {
+  std::vector<std::function<void()>> bodies(1, std::move(body));
+  return launch_all(1, grid, block, bodies);
+}
+
+template <int W>
+void run_exch(const ExParams& P, bool bf16, bool nvls, bool inplace) {
+  if (inplace) { if (nvls) exch_kernel<W, false, true, true>(P); else exch_kernel<W, false, false, true>(P); }
+  else if (bf16) { if (nvls) exch_kernel<W, true, true, false>(P); else exch_kernel<W, true, false, false>(P); }
+  else { if (nvls) exch_kernel<W, false, true, false>(P); else exch_kernel<W, false, false, false>(P); }
+}
+void run_exch_w(int world, bool generic, const ExParams& P, bool bf16, bool nvls, bool inplace) {
+  if (generic) return run_exch<0>(P, bf16, nvls, inplace);
+  switch (world) {
+    case 2: return run_exch<2>(P, bf16, nvls, inplace);
+    case 4: return run_exch<4>(P, bf16, nvls, inplace);
+    case 8: return run_exch<8>(P, bf16, nvls, inplace);
+    default: return run_exch<0>(P, bf16, nvls, inplace);
   }
 }
 
@@ -117,7 +135,85 @@ void emu_group_destroy(void* h) {
 
 size_t emu_signal_bytes(void) { return kSignalBytes; }
 
-// bufs[r]: rank r's fp32 bucket, reduced in place.  algo: 1 one-shot, 2 two-shot, 3 two-shot NVLS, 5/6 pipelined.
+// The staged exchange (b2d_staged.cuh) of one bucket, cut into chunks of `chunk_packs`, epochs epoch0.. (monotone
+// over calls, like ctx->epoch in b2d.cu).  wire_off: byte offset of the staging region in every arena; with
+// `inplace` the fp32 buckets themselves live there (bufs is ignored).  `order`:
+//   0  every rank is one in-order stream S,X,W,U per chunk; the ranks run concurrently
+//   1  fully serialised, phase-major (S of every rank, then X of every rank, then W+U): what a serialising
+//      profiler makes of the single-GPU loopback ranks
+//   2  three concurrent streams per rank (all S | all X | all W+U), coupled ONLY by the staged / published
+//      flags — more freedom than the event-ordered streams of b2d.cu allow
+int emu_staged_allreduce(void* h, int nvls, int bf16, int inplace, float** bufs, size_t n, float scale, size_t wire_off,
+                         size_t chunk_packs, int st_grid, int ex_grid, unsigned epoch0, int order, int use_generic_w) {
+  Group* g = static_cast<Group*>(h);
+  const int world = g->world;
+  const size_t epp = bf16 ? 8 : 4;
+  const size_t npacks = (n + epp - 1) / epp;
+  if (wire_off + npacks * 16 > g->arena_bytes) return -4;
+  const int nchunks = static_cast<int>((npacks + chunk_packs - 1) / chunk_packs);
+  emu::Multicast& mc = emu::multicast();
+  mc.fake_base = g->fake_mc; mc.world = world;
+  for (int r = 0; r < world; ++r) mc.arena[r] = g->arena[r];
+  const Peers peers = make_peers(*g);
+  auto S = [&](int r, int c) {
+    StParams P{};
+    P.scale = scale; P.rank = r; P.world = world; P.peers = peers;
+    const size_t p0 = static_cast<size_t>(c) * chunk_packs, pc = npacks - p0 < chunk_packs ? npacks - p0 : chunk_packs;
+    if (inplace) {
+      if (c != 0) return 0;
+      P.epoch = epoch0 + nchunks - 1;
+      return launch_one(1, 32, [P] { arrive_kernel(P); });
+    }
+    P.grad = bufs[r] + p0 * epp;
+    P.n = (p0 + pc) * epp <= n ? pc * epp : n - p0 * epp;
+    P.wire = reinterpret_cast<uint4*>(g->arena[r] + wire_off) + p0;
+    P.epoch = epoch0 + c;
+    return bf16 ? launch_one(st_grid, kStThreads, [P] { stage_kernel<true>(P); }) : launch_one(st_grid, kStThreads, [P] { stage_kernel<false>(P); });
+  };
+  auto X = [&](int r, int c) {
+    ExParams P{};
+    P.scale = scale; P.rank = r; P.world = world; P.peers = peers; P.timeout_ns = 120ull * 1000000000ull; P.diag = nullptr;
+    const size_t p0 = static_cast<size_t>(c) * chunk_packs, pc = npacks - p0 < chunk_packs ? npacks - p0 : chunk_packs;
+    P.wire_off = wire_off + p0 * 16; P.npacks = pc; P.epoch = epoch0 + c;
+    P.n_valid = inplace ? (n - p0 * 4 < pc * 4 ? n - p0 * 4 : pc * 4) : 0;
+    return launch_one(ex_grid, kExThreads, [=] { run_exch_w(world, use_generic_w != 0, P, bf16 != 0, nvls != 0, inplace != 0); });
+  };
+  auto WU = [&](int r, int c) {
+    ExParams P{};
+    P.rank = r; P.world = world; P.peers = peers; P.timeout_ns = 120ull * 1000000000ull; P.epoch = epoch0 + c;
+    int rc = launch_one(1, 32, [P] { wait_published_kernel(P); });
+    if (rc != 0 || inplace) return rc;
+    StParams Q{};
+    Q.scale = scale; Q.rank = r; Q.world = world; Q.peers = peers;
+    const size_t p0 = static_cast<size_t>(c) * chunk_packs, pc = npacks - p0 < chunk_packs ? npacks - p0 : chunk_packs;
+    Q.grad = bufs[r] + p0 * epp;
+    Q.n = (p0 + pc) * epp <= n ? pc * epp : n - p0 * epp;
+    Q.wire = reinterpret_cast<uint4*>(g->arena[r] + wire_off) + p0;
+    Q.epoch = epoch0 + c;
+    return bf16 ? launch_one(st_grid, kStThreads, [Q] { unstage_kernel<true>(Q); }) : launch_one(st_grid, kStThreads, [Q] { unstage_kernel<false>(Q); });
+  };
+  std::atomic<int> bad{0};
+  if (order == 1) {
+    for (int c = 0; c < nchunks; ++c) for (int r = 0; r < world; ++r) if (S(r, c) != 0) return -1;
+    for (int c = 0; c < nchunks; ++c) for (int r = 0; r < world; ++r) if (X(r, c) != 0) return -1;
+    for (int c = 0; c < nchunks; ++c) for (int r = 0; r < world; ++r) if (WU(r, c) != 0) return -1;
+    return 0;
+  }
+  std::vector<std::thread> streams;
+  for (int r = 0; r < world; ++r) {
+    if (order == 0) {
+      streams.emplace_back([&, r] { for (int c = 0; c < nchunks; ++c) if (S(r, c) != 0 || X(r, c) != 0 || WU(r, c) != 0) bad = 1; });
+    } else {
+      streams.emplace_back([&, r] { for (int c = 0; c < nchunks; ++c) if (S(r, c) != 0) bad = 1; });
+      streams.emplace_back([&, r] { for (int c = 0; c < nchunks; ++c) if (X(r, c) != 0) bad = 1; });
+      streams.emplace_back([&, r] { for (int c = 0; c < nchunks; ++c) if (WU(r, c) != 0) bad = 1; });
+    }
+  }
+  for (auto& t : streams) t.join();
+  return bad.load() ? -1 : 0;
+}
+
+// bufs[r]: rank r's fp32 bucket, reduced in place.  algo: 1 one-shot, 2 two-shot, 3 two-shot NVLS (fused).
 // parity selects the half of the (single) double-buffered slot, exactly like get_slot() in b2d.cu.
 int emu_allreduce(void* h, int algo, int bf16, float** bufs, size_t n, float scale, int grid, int parity, int use_generic_w,
                   int pipe_k) {

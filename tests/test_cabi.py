@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = _b2d.load()
     for name in _declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.b2d_version() == 100
+    assert lib.b2d_version() == 110
 
 
 def test_handle_blob_size_matches_header():

@@ -23,7 +23,7 @@ FP = ctypes.POINTER(ctypes.c_float)
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("emu") / "libb2d_emu.so")
-    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DB2D_EMU", "-DB2D_EMU_WITH_PIPE", "-ffp-contract=off",
+    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-shared", "-DB2D_EMU", "-ffp-contract=off",
                     "-o", out, os.path.join(EMU_DIR, "emu_harness.cpp")], check=True)
     lib = ctypes.CDLL(out)
     lib.emu_group_create.restype = ctypes.c_void_p
@@ -32,6 +32,9 @@ def emu(tmp_path_factory):
     lib.emu_signal_bytes.restype = ctypes.c_size_t
     lib.emu_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(FP), ctypes.c_size_t,
                                   ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.emu_staged_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(FP),
+                                         ctypes.c_size_t, ctypes.c_float, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_int]
     lib.emu_k0.argtypes = [FP, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_int]
     lib.emu_sharded_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(FP), ctypes.c_size_t, ctypes.POINTER(FP),
                                      ctypes.POINTER(FP), ctypes.c_size_t, ctypes.POINTER(ctypes.c_longlong), ctypes.c_float,
@@ -131,42 +134,94 @@ def test_sharded_step_on_cpu_threads(emu, world, generic, bf16):
         emu.emu_group_destroy(g)
 
 
-@pytest.mark.parametrize("world,grid", [(2, 2), (4, 2), (8, 1)])
-@pytest.mark.parametrize("algo", [5, 6])
-@pytest.mark.parametrize("pipe_k", [1, 2])
-def test_pipelined_kernel_on_cpu_threads(emu, world, grid, algo, pipe_k):
-    """K2P (three concurrent warp roles coupled by monotone counters), P2P and NVLS variants: several chunks per
-    block (run = 128 packs, chunk = pipe_k runs), ragged sizes, consecutive launches on alternating halves."""
-    g = emu.emu_group_create(world, 8 << 20)
+@pytest.mark.parametrize("world,generic", [(2, 0), (4, 0), (8, 0), (3, 1)])
+@pytest.mark.parametrize("nvls", [0, 1])
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_staged_exchange_on_cpu_threads(emu, world, generic, nvls, order):
+    """K7-K10 (stage | exchange | wait + write back as separate kernels, b2d_staged.cuh), P2P and NVLS (switch
+    emulated), both wires, one to several chunks, ragged sizes; consecutive calls keep the monotone epochs and
+    alternate the staging half.  order 1 runs every kernel of every rank strictly one after the other, phase-major:
+    the schedule a serialising profiler imposes on the loopback ranks must complete too."""
+    sig = emu.emu_signal_bytes()
+    g = emu.emu_group_create(world, 4 << 20)
     try:
-        step = 0
+        epoch, step = 1, 0
+        chunk = 1024 * world if world != 3 else 1026
         for bf16 in (1, 0):
-            for n in (1, 9, 4099, 20011, 70001):
-                per_rank = inputs(world, n, 50 * step + algo)
+            for n in (1, 9, 4099, 20011, 40003):
+                per_rank = inputs(world, n, 70 * step + nvls)
                 bufs = [t.numpy().copy() for t in per_rank]
                 scale = float(np.float32(1.0) / np.float32(world))
-                assert emu.emu_allreduce(g, algo, bf16, ptrs(bufs), n, scale, grid, step & 1, 0, pipe_k) == 0
+                npacks = -(-n // (8 if bf16 else 4))
+                half = (step & 1) * (1 << 20)
+                rc = emu.emu_staged_allreduce(g, nvls, bf16, 0, ptrs(bufs), n, scale, sig + half, chunk, 1, 1, epoch, order, generic)
+                assert rc == 0
+                epoch += -(-npacks // chunk)
                 want = (ddp_oracle.allreduce_bf16_wire if bf16 else ddp_oracle.allreduce_fp32_wire)(per_rank).numpy()
                 for r in range(world):
-                    assert same_bits(bufs[r], want), (world, algo, bf16, n, r, pipe_k)
+                    assert same_bits(bufs[r], want), (world, nvls, bf16, n, r, order)
                 step += 1
     finally:
         emu.emu_group_destroy(g)
 
 
-@pytest.mark.parametrize("algo", [2, 5, 6])
+@pytest.mark.parametrize("world,generic", [(2, 0), (4, 0), (3, 1)])
+@pytest.mark.parametrize("nvls", [0, 1])
+def test_staged_exchange_in_place_on_cpu_threads(emu, world, generic, nvls):
+    """fp32 buckets that LIVE in the arena (f-1): no stage, no write back; the exchange scales and reduces the
+    bucket where it is, ragged last pack included (element-wise path)."""
+    sig = emu.emu_signal_bytes()
+    g = emu.emu_group_create(world, 4 << 20)
+    try:
+        epoch = 1
+        for step, n in enumerate((1, 2, 7, 4099, 4100, 20011)):
+            per_rank = inputs(world, n, 33 * step + nvls)
+            views = []
+            for r in range(world):
+                v = np.ctypeslib.as_array(emu.emu_arena_ptr(g, r, sig + 4096), shape=(n + 8,))
+                v[:] = 777.0                       # a neighbour's bytes past the end must survive
+                v[:n] = per_rank[r].numpy()
+                views.append(v)
+            scale = float(np.float32(1.0) / np.float32(world))
+            chunk = 1024 * world if world != 3 else 1026
+            assert emu.emu_staged_allreduce(g, nvls, 0, 1, None, n, scale, sig + 4096, chunk, 1, 1, epoch, 2 if step % 2 else 0, generic) == 0
+            epoch += -(-(-(-n // 4)) // chunk)
+            want = ddp_oracle.allreduce_fp32_wire(per_rank, scale).numpy()
+            for r in range(world):
+                if nvls and world & (world - 1):
+                    # the switch adds the RAW values and the kernel scales the sum: (sum g) / W rounds differently from
+                    # sum (g / W) unless W is a power of two — the NVLS tolerance contract (north star: rtol 1e-3 / atol 1e-5)
+                    np.testing.assert_allclose(views[r][:n], want, rtol=1e-5, atol=1e-7)
+                    assert same_bits(views[r][:n], views[0][:n])
+                else:
+                    assert same_bits(views[r][:n], want), (world, nvls, n, r)
+                assert float(views[r][n]) == 777.0 and float(views[r][n + 3]) == 777.0
+    finally:
+        emu.emu_group_destroy(g)
+
+
+@pytest.mark.parametrize("algo", [2, 5])
 def test_kernels_with_scheduling_jitter(emu, algo, monkeypatch):
-    """Random 0-300 us sleeps at 2 % of all barrier entries (B2D_EMU_JITTER): roles, blocks and ranks drift far apart;
-    six consecutive launches on alternating halves must still match the oracle bit for bit."""
+    """Random 0-300 us sleeps at 2 % of all barrier entries (B2D_EMU_JITTER): blocks and ranks drift far apart;
+    six consecutive launches on alternating halves must still match the oracle bit for bit (5 = staged exchange,
+    three flag-coupled streams per rank)."""
     monkeypatch.setenv("B2D_EMU_JITTER", "20")
     world, grid = 4, 2
+    sig = emu.emu_signal_bytes()
     g = emu.emu_group_create(world, 8 << 20)
     try:
+        epoch = 1
         for step in range(6):
             n = 30011 + 997 * step
             per_rank = inputs(world, n, 900 + step)
             bufs = [t.numpy().copy() for t in per_rank]
-            assert emu.emu_allreduce(g, algo, 1, ptrs(bufs), n, 0.25, grid, step & 1, 0, 1) == 0
+            if algo == 5:
+                chunk = 1024 * world
+                assert emu.emu_staged_allreduce(g, 0, 1, 0, ptrs(bufs), n, 0.25, sig + (step & 1) * (1 << 20), chunk, 2, 2,
+                                                epoch, 2, 0) == 0
+                epoch += -(-(-(-n // 8)) // chunk)
+            else:
+                assert emu.emu_allreduce(g, algo, 1, ptrs(bufs), n, 0.25, grid, step & 1, 0, 1) == 0
             want = ddp_oracle.allreduce_bf16_wire(per_rank).numpy()
             for r in range(world):
                 assert same_bits(bufs[r], want), (algo, step, r)
