@@ -28,7 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "images/sec, ResNet-50 RayStrategy (+ allreduce bus GB/s)"
-NVLINK_PEAK_GBS = 770.0   # /opt/skills/guides/B200_PROFILING.md: measured peer copy per direction (fallback: not in MEASURED_PEAKS.json)
+NVLINK_NOMINAL_GBS = 900.0    # NVLink 5, per direction per GPU
+NVLINK_FALLBACK_GBS = 770.0   # /opt/skills/guides/B200_PROFILING.md: measured peer copy — used only if the in-run probe fails
 
 
 def parse():
@@ -39,7 +40,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: 64 resnet, 16 bert, 4 gpt2)")
     ap.add_argument("--bucket-cap-mb", type=int, default=25)
-    ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16 = BASELINE.json's configuration (the strategy's own default is the reference's fp32)")
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--mem", default="vmm", choices=["vmm", "ipc"])
     ap.add_argument("--max-ctas", type=int, default=None)
@@ -50,6 +52,11 @@ def parse():
                     help="b200 = libb2d; nccl_* = the reference's GPU path through the same strategy (A/B)")
     ap.add_argument("--seq", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity block (N > 1)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the short allreduce sweep vs NCCL / symm_mem (N > 1)")
+    ap.add_argument("--chunk-mb", type=int, default=None, help="staged exchange: wire MiB per pipeline chunk")
+    ap.add_argument("--exch-ctas", type=int, default=None)
+    ap.add_argument("--no-arena-buckets", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8)
     return ap.parse_args()
 
@@ -165,6 +172,213 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---- multi-GPU evidence that rides along with the bench line (outside every timed region) -----------------
+def link_probe(comm, dist, torch, world, rank):
+    """What ONE GPU pulls from ONE peer, measured here and now: cudaMemcpyAsync and a peer-read kernel with the
+    library's own 16-byte access pattern, every rank pulling from its right neighbour at the same time."""
+    out = {"nominal_GBps": NVLINK_NOMINAL_GBS}
+    try:
+        peer = (rank + 1) % world
+        vals = []
+        for mode in (0, 1):
+            dist.barrier()
+            v = comm.ctx.peer_bw(peer, 128 << 20, iters=8, mode=mode)
+            t = torch.tensor([v], device="cuda")
+            lo = t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            vals.append((float(lo), float(t) / world))
+        out.update({"memcpy_peer_GBps_min": round(vals[0][0], 1), "memcpy_peer_GBps_mean": round(vals[0][1], 1),
+                    "peer_read_kernel_GBps_min": round(vals[1][0], 1), "peer_read_kernel_GBps_mean": round(vals[1][1], 1),
+                    "how": "128 MiB x 8 from the right neighbour's arena, all ranks at once, CUDA events (b2d_peer_bw)"})
+        out["peak_GBps"] = round(max(vals[0][1], vals[1][1]), 1)
+        out["source"] = "measured in this run"
+    except Exception as e:
+        out.update({"peak_GBps": NVLINK_FALLBACK_GBS, "source": "fallback (B200_PROFILING.md peer copy); probe failed: %r" % (e,)})
+    return out
+
+
+def parity_block(comm, dist, torch, world, rank, dev, bucket_sizes):
+    """Every algorithm the library exports, on seeded buckets of the step's own sizes + ragged ones, against the
+    oracle (bit for bit for the P2P algorithms, stated tolerance for NVLS) and against NCCL on the same inputs."""
+    import numpy as np
+    from oracle import ddp_oracle        # the checker, never the thing measured
+    sizes = sorted(set(list(bucket_sizes) + [1, 4099, (1 << 20) + 5]))
+    algos = ["one_shot", "two_shot", "two_shot_tma", "staged"] + (["nvls", "nvls_fused"] if comm.nvls else [])
+    scale = float(np.float32(1.0) / np.float32(world))
+    failed, cases = [], 0
+    key = 20000
+    worst = {"fp32_vs_nccl_max_abs": 0.0, "bf16_err_vs_exact_libb2d": 0.0, "bf16_err_vs_exact_nccl": 0.0,
+             "nvls_bf16_ulps_max": 0.0}
+
+    def bits_equal(a, b):
+        return torch.equal(a.view(torch.int32), b.view(torch.int32))
+
+    for n in sizes:
+        per_rank = [torch.randn(n, generator=torch.Generator().manual_seed(4242 + 131 * r + n % 1009)) * 2.0 ** -4 for r in range(world)]
+        mine = per_rank[rank].to(dev)
+        want = {"bf16": ddp_oracle.allreduce_bf16_wire(per_rank), "fp32": ddp_oracle.allreduce_fp32_wire(per_rank)}
+        exact_bf = sum(ddp_oracle.wire_bf16(t, scale).double() for t in per_rank)
+        # the reference's GPU path on the same inputs
+        nccl_fp32 = mine / world
+        dist.all_reduce(nccl_fp32)
+        c = mine.to(torch.bfloat16).div_(world)
+        dist.all_reduce(c)
+        nccl_bf16 = c.float()
+        torch.cuda.synchronize()
+        worst["bf16_err_vs_exact_nccl"] = max(worst["bf16_err_vs_exact_nccl"], float((nccl_bf16.cpu().double() - exact_bf).abs().max()))
+        for wire in ("bf16", "fp32"):
+            for algo in algos:
+                if algo == "two_shot_tma" and (wire != "bf16" or n % 8):
+                    continue
+                if algo == "one_shot" and n > (4 << 20):
+                    continue
+                cases += 1
+                buf = mine.clone()
+                # one arena slot per (size, wire): a change of algorithm re-fences and re-uses the region
+                comm.allreduce_(buf, bucket_idx=key + 2 * sizes.index(n) + (wire == "bf16"), wire=wire, algo=algo)
+                torch.cuda.synchronize()
+                got = buf.cpu()
+                tag = "%s/%s/n=%d" % (algo, wire, n)
+                if algo.startswith("nvls"):
+                    # every rank must hold the same bits; value within the stated tolerance
+                    h = torch.tensor([int(got.view(torch.int32).long().sum().item()) & 0x7fffffffffff], device=dev)
+                    lo, hi = h.clone(), h.clone()
+                    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                    ok = int(lo) == int(hi)
+                    if wire == "fp32":
+                        ok = ok and torch.allclose(got, want["fp32"], rtol=1e-5, atol=1e-8)
+                    else:
+                        d = (got.double() - exact_bf).abs()
+                        ulp = torch.maximum(got.double().abs(), exact_bf.abs()) * 2.0 ** -7
+                        ok = ok and bool((d <= ulp + 1e-30).all())
+                        worst["nvls_bf16_ulps_max"] = max(worst["nvls_bf16_ulps_max"], float((d / (ulp + 1e-30)).max()))
+                else:
+                    ok = bits_equal(got, want[wire])
+                if wire == "fp32":
+                    ok = ok and torch.allclose(got, nccl_fp32.cpu(), rtol=1e-3, atol=1e-5)   # north-star tolerance vs the NCCL path
+                    worst["fp32_vs_nccl_max_abs"] = max(worst["fp32_vs_nccl_max_abs"], float((got - nccl_fp32.cpu()).abs().max()))
+                else:
+                    e = float((got.double() - exact_bf).abs().max())
+                    worst["bf16_err_vs_exact_libb2d"] = max(worst["bf16_err_vs_exact_libb2d"], e)
+                if not ok:
+                    failed.append(tag)
+    # one fused sharded step (reduce-scatter -> Adam -> all-gather) against the oracle's Adam on the averaged gradients
+    try:
+        total = 8 * 1024 * world
+        shard_off = [i * 8 * 1024 for i in range(world + 1)]
+        p0 = torch.randn(total, generator=torch.Generator().manual_seed(99)) * 0.05
+        per_rank = [torch.randn(total, generator=torch.Generator().manual_seed(300 + r)) * 0.05 for r in range(world)]
+        params = comm.arena_tensor(total)
+        params.copy_(p0.to(dev))
+        m, v = torch.zeros(8 * 1024, device=dev), torch.zeros(8 * 1024, device=dev)
+        g = per_rank[rank].to(dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        comm.sharded_step_(g, params, m, v, shard_off, step=1, lr=1e-2, wire="fp32", slot=7)
+        torch.cuda.synchronize()
+        avg = ddp_oracle.allreduce_fp32_wire(per_rank, scale)
+        pn, mn, vn = p0.numpy().copy(), np.zeros(total, np.float32), np.zeros(total, np.float32)
+        ddp_oracle.adam_step(pn, avg.numpy(), mn, vn, 1, 1e-2)
+        cases += 1
+        if not np.allclose(params.cpu().numpy(), pn, rtol=2e-5, atol=2e-6):
+            failed.append("sharded_step/fp32")
+    except Exception as e:
+        failed.append("sharded_step raised %r" % (e,))
+    flag = torch.tensor([0 if failed else 1], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, failed[:8])
+    return {"all_ok": bool(int(flag) == 1), "cases_per_rank": cases, "algos": algos, "sizes": sizes, "nvls_bound": bool(comm.nvls),
+            "failed": sorted(set(x for f in gathered for x in f))[:16],
+            "contract": "P2P algorithms bit-exact vs oracle.ddp_oracle (both wires); NVLS: all ranks same bits, fp32 rtol 1e-5, "
+                        "bf16 within one bf16 step of the exact sum; fp32 wire vs ncclAllReduce rtol 1e-3 / atol 1e-5",
+            **{k: float("%.3g" % v) for k, v in worst.items()},
+            "bf16_libb2d_not_worse_than_nccl": worst["bf16_err_vs_exact_libb2d"] <= worst["bf16_err_vs_exact_nccl"] + 1e-12}
+
+
+def allreduce_sweep(comm, dist, torch, world, rank, sizes, iters=20, symm=True):
+    """Isolated allreduce of `sizes` (bytes of bf16 wire payload) back to back on one stream: libb2d (whole fused op:
+    cast + scale + exchange + write-back) next to ncclAllReduce alone, the reference's bf16 hook sequence, and
+    torch.ops.symm_mem.* on a symmetric bf16 buffer.  ms = max over ranks of the per-iteration average."""
+    rows = []
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        b.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / iters], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    sm_state = {}
+    if symm:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            gname = dist.group.WORLD.group_name
+            try:
+                symm_mem.enable_symm_mem_for_group(gname)
+            except Exception:
+                pass
+            sm_state = {"mod": symm_mem, "group": gname}
+        except Exception as e:
+            sm_state = {"error": repr(e)}
+    key = 30000
+    for wire_bytes in sizes:
+        n = wire_bytes // 2
+        buf = torch.randn(n, device="cuda") * 0.01
+        row = {"wire_bytes": wire_bytes, "elements": n}
+        algos = ["auto", "one_shot", "two_shot", "staged"] + (["nvls", "nvls_fused"] if comm.nvls else [])
+        for algo in algos:
+            if algo == "one_shot" and wire_bytes > (16 << 20):
+                continue
+            k = key + sizes.index(wire_bytes)
+            try:
+                row["b2d_" + algo + "_ms"] = round(timed(lambda: comm.allreduce_(buf, bucket_idx=k, wire="bf16", algo=algo)), 4)
+            except Exception as e:
+                row["b2d_" + algo + "_error"] = repr(e)[:120]
+        row["auto_algo"] = comm.ctx.plan(n, 1)[0]
+
+        def hook_seq():
+            c = buf.to(torch.bfloat16).div_(world)
+            dist.all_reduce(c)
+            buf.copy_(c)
+        row["nccl_bf16_hook_seq_ms"] = round(timed(hook_seq), 4)
+        cb = buf.to(torch.bfloat16)
+        row["nccl_bf16_allreduce_only_ms"] = round(timed(lambda: dist.all_reduce(cb)), 4)
+        if "mod" in sm_state:
+            try:
+                t = sm_state["mod"].empty(n, dtype=torch.bfloat16, device="cuda")
+                sm_state["mod"].rendezvous(t, sm_state["group"])
+                t.copy_(cb)
+                for name, op in (("one_shot", "one_shot_all_reduce"), ("two_shot", "two_shot_all_reduce_"), ("multimem", "multimem_all_reduce_")):
+                    if name == "one_shot" and wire_bytes > (16 << 20):
+                        continue
+                    try:
+                        f = getattr(torch.ops.symm_mem, op)
+                        row["symm_mem_%s_ms" % name] = round(timed(lambda: f(t, "sum", sm_state["group"])), 4)
+                    except Exception as e:
+                        row["symm_mem_%s_error" % name] = repr(e)[:120]
+            except Exception as e:
+                row["symm_mem_error"] = repr(e)[:160]
+        elif "error" in sm_state:
+            row["symm_mem_error"] = sm_state["error"][:160]
+        bus = 2.0 * (world - 1) / world * wire_bytes
+        for k2 in [k for k in row if k.endswith("_ms")]:
+            row[k2[:-3] + "_busGBps"] = round(bus / row[k2] / 1e6, 1)
+        rows.append(row)
+        del buf, cb
+    return rows
+
+
 # ---- our arm -----------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -241,7 +455,9 @@ def run_b200(args):
     # the worker-side call sequence of RayLauncher._wrapping_function (launchers/ray_launcher.py)
     from ray_lightning_b200 import RayShardedStrategy
     kw = dict(num_workers=world, use_gpu=True, b200_wire=args.wire, b200_algo=args.algo, b200_mem=args.mem,
-              b200_timing=True, b200_max_ctas=args.max_ctas)
+              b200_timing=True, b200_max_ctas=args.max_ctas, b200_exch_ctas=args.exch_ctas,
+              b200_chunk_bytes=(args.chunk_mb << 20) if args.chunk_mb else None,
+              b200_arena_buckets=not args.no_arena_buckets)
     if args.strategy == "sharded":
         strategy = RayShardedStrategy(**kw)
     else:
@@ -322,6 +538,9 @@ def run_b200(args):
     st = comm.stats() if comm is not None else {"launches": 0, "timed_ms": 0.0, "timed_launches": 0}
     launches_timed, kernel_ms = int(st["launches"]), float(st["timed_ms"])
     timed_launches = int(st["timed_launches"])
+    # the staged exchange times its NVLink kernel (the only one that can wait for a peer) on its own stream
+    exch_ms, exch_timed, exch_launches = float(st.get("exch_ms", 0.0)), int(st.get("exch_timed", 0)), int(st.get("exch_launches", 0))
+    last_algo = int(st.get("last_algo", 0))
     e2e_ms, last_loss = timed(args.steps, e2e=True)
 
     # The same buckets once more, ISOLATED (no backward running, ranks aligned by a barrier): what the
@@ -351,6 +570,22 @@ def run_b200(args):
             isolated.append((idx, n, float(t)))
         barrier()
 
+    link = parity = sweep = None
+    if world > 1 and comm is not None and args.hook == "b200":
+        link = link_probe(comm, dist, torch, world, rank)
+        if not args.no_parity:
+            try:
+                parity = parity_block(comm, dist, torch, world, rank, dev,
+                                      sorted(state.seen.values()) if state is not None and state.seen else [])
+            except Exception as e:
+                parity = {"all_ok": False, "error": repr(e)[:300]}
+        if not args.no_sweep:
+            try:
+                sweep = allreduce_sweep(comm, dist, torch, world, rank, [64 << 10, 1 << 20, 16 << 20, 64 << 20])
+            except Exception as e:
+                sweep = [{"error": repr(e)[:300]}]
+        barrier()
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         ms_per_step = total_ms / args.steps
@@ -370,8 +605,14 @@ def run_b200(args):
             alg_bytes_step = 2.0 * (world - 1) / world * n_params * wire_w   # NCCL-tests bus-bandwidth convention
             if args.strategy == "sharded":   # reduce-scatter at wire width + fp32 parameter all-gather
                 alg_bytes_step = (world - 1) / world * n_params * (wire_w + 4.0)
-            bound, peak, runit = "nvlink", NVLINK_PEAK_GBS, "GB/s"
-            peak_note = "fallback: B200_PROFILING.md measured peer copy 770 GB/s per direction (not in MEASURED_PEAKS.json)"
+            bound, runit = "nvlink", "GB/s"
+            peak = float(link["peak_GBps"]) if link else NVLINK_FALLBACK_GBS
+            peak_note = "peer link probe, %s (nominal %.0f GB/s per direction)" % (link["source"] if link else "fallback", NVLINK_NOMINAL_GBS)
+            if exch_timed > 0 and args.strategy != "sharded":
+                # staged exchange: the dominant kernel is the exchange kernel, timed per bucket on its own stream
+                kernel_ms, timed_launches = exch_ms, exch_timed
+                per_launch_ms = kernel_ms / max(timed_launches, 1)
+                buckets_per_step = exch_timed / args.steps
         achieved = alg_bytes_step * args.steps / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else None
         traffic = None
         try:
@@ -392,7 +633,8 @@ def run_b200(args):
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
                        "bucket_cap_mb": args.bucket_cap_mb, "grad_elements": n_params,
                        "l2_policy": "inputs larger than L2 (activations + 97.5 MiB of gradients per step >> 126 MB)",
-                       "algo": args.algo, "mem": args.mem, "nvls_bound": bool(getattr(comm, "nvls", False)),
+                       "algo": args.algo, "algo_used": last_algo, "mem": args.mem, "nvls_bound": bool(getattr(comm, "nvls", False)),
+                       "arena_buckets": bool(getattr(strategy, "b200_arena_buckets_active", False)),
                        "strategy": args.strategy, "hook": args.hook},
             "e2e": {"value": round(e2e_value, 2), "unit": unit + "/sec", "ms_per_step": round(e2e_ms / args.steps, 3),
                     "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)) * world,
@@ -402,11 +644,20 @@ def run_b200(args):
             "roofline": {"bound": bound, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": runit,
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                          "kernel": ("k456_sharded_kernel" if args.strategy == "sharded" else
-                                    "k0_cast_scale_kernel<bf16>" if world == 1 else "k1/k2 fused allreduce") if args.hook == "b200" else None,
+                                    "k0_cast_scale_kernel<bf16>" if world == 1 else
+                                    {3: "exch_kernel<NVLS> (staged exchange, multimem.ld_reduce + multimem.st)",
+                                     5: "exch_kernel<P2P> (staged exchange, peer loads + peer stores)"}.get(last_algo, "k1/k2 fused allreduce"))
+                                   if args.hook == "b200" else None,
                          "algorithmic_bytes_per_step": alg_bytes_step, "launches_per_step": buckets_per_step,
                          "avg_launch_ms": round(per_launch_ms, 5), "kernel_share_of_step": round(kernel_ms / total_ms, 5),
                          "peak_source": peak_note,
-                         "note": "launch durations from CUDA events on the comm stream inside the timed region (overlapped with backward)"},
+                         "frac_of_nominal_900": (round(achieved / NVLINK_NOMINAL_GBS, 4) if achieved and world > 1 else None),
+                         "link_level": (None if world == 1 or not achieved or last_algo != 3 else {
+                             "note": "in-switch reduction: bytes that really cross one GPU's links per direction = (1 + 1/W) x N x w",
+                             "GBps": round(achieved * (1.0 + 1.0 / world) / (2.0 * (world - 1) / world), 1),
+                             "frac": round(achieved * (1.0 + 1.0 / world) / (2.0 * (world - 1) / world) / peak, 4)}),
+                         "note": "launch durations from CUDA events on the launching stream inside the timed region (overlapped with backward); "
+                                 "achieved = NCCL-tests bus bytes 2(W-1)/W x N x w per step / summed exchange-kernel time"},
             "clocks": clocks, "final_loss": last_loss if isinstance(last_loss, float) else float(last_loss),
             "allreduce_isolated": None if not isolated else {
                 "note": "same bucket sizes, back to back on the comm stream with no backward running (L2-warm), max over ranks",
@@ -417,7 +668,10 @@ def run_b200(args):
                                         for _, n, _ in isolated) / sum(ms for _, _, ms in isolated) / 1e6, 1),
                 "unit": "HBM GB/s (8 B/element)" if world == 1 else "NVLink bus GB/s (2(W-1)/W x wire bytes)"},
         }
-        if not args.no_cpu_baseline and world == 1 and args.model.startswith("resnet"):
+        line["nvlink"] = link
+        line["parity"] = parity
+        line["allreduce_sweep"] = sweep
+        if not args.no_cpu_baseline and args.model.startswith("resnet"):
             try:
                 cb = cpu_reference(1, args.cpu_batch, 2, 1, args.model)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

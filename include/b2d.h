@@ -147,6 +147,7 @@ int b2d_ctx_set_tma_ctas(b2d_ctx* ctx, int ctas);            /* CTAs of the TMA-
 int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes); /* AUTO: one-shot at or below */
 int b2d_ctx_set_chunk_bytes(b2d_ctx* ctx, size_t wire_bytes);  /* staged exchange: wire bytes per pipeline chunk; default 32 MiB */
 int b2d_ctx_set_exch_ctas(b2d_ctx* ctx, int ctas);             /* CTAs of the exchange kernel; default 32 */
+int b2d_ctx_set_inplace(b2d_ctx* ctx, int enable);             /* exchange arena-resident fp32 buckets in place? default 1 */
 int b2d_ctx_set_nvls_auto(b2d_ctx* ctx, int enable);           /* may AUTO pick B2D_ALGO_NVLS when multicast is bound? default 1 */
 
 /* ---- data path ------------------------------------------------------------------------- */
@@ -259,6 +260,8 @@ typedef struct b2d_stats {
   uint64_t exch_launches;  /* exchange kernels (staged algorithms) launched */
   uint64_t exch_timed;     /* bucket exchanges bracketed by events (B2D_FLAG_TIMING) and resolved */
   double exch_ms;          /* sum of their device durations (first exchange kernel start .. last end) */
+  uint64_t pool_allocs;    /* b2d_pool_alloc calls served */
+  uint64_t pool_digest;    /* FNV-1a over their (offset, size): equal on every rank <=> bucket storage is symmetric */
 } b2d_stats;
 
 int b2d_ctx_stats(b2d_ctx* ctx, b2d_stats* out);   /* resolves finished timing events */

@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "b2d_allgather", "b2d_barrier", "b2d_arena_alloc", "b2d_arena_reset", "b2d_ctx_stats",
     "b2d_ctx_reset_stats", "b2d_plan", "b2d_ctx_trace", "b2d_ctx_set_tma_ctas",
     "b2d_allreduce_bucket_phased", "b2d_ctx_set_chunk_bytes", "b2d_ctx_set_exch_ctas", "b2d_ctx_set_nvls_auto",
-    "b2d_peer_bw", "b2d_pool_bind", "b2d_pool_alloc", "b2d_pool_free",
+    "b2d_peer_bw", "b2d_pool_bind", "b2d_pool_alloc", "b2d_pool_free", "b2d_ctx_set_inplace",
 ]
 
 
@@ -59,7 +59,8 @@ class Stats(ctypes.Structure):
                 ("device", ctypes.c_int32), ("sm_count", ctypes.c_int32), ("mem_kind", ctypes.c_int32),
                 ("mc_bound", ctypes.c_int32), ("last_algo", ctypes.c_int32), ("last_grid", ctypes.c_int32),
                 ("last_block", ctypes.c_int32), ("pad_", ctypes.c_int32), ("exch_launches", ctypes.c_uint64),
-                ("exch_timed", ctypes.c_uint64), ("exch_ms", ctypes.c_double)]
+                ("exch_timed", ctypes.c_uint64), ("exch_ms", ctypes.c_double), ("pool_allocs", ctypes.c_uint64),
+                ("pool_digest", ctypes.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -96,6 +97,7 @@ def _declare(lib):
         "b2d_ctx_set_chunk_bytes": [vp, sz],
         "b2d_ctx_set_exch_ctas": [vp, c.c_int],
         "b2d_ctx_set_nvls_auto": [vp, c.c_int],
+        "b2d_ctx_set_inplace": [vp, c.c_int],
         "b2d_peer_bw": [vp, c.c_int, sz, c.c_int, c.c_int, c.POINTER(c.c_double)],
         "b2d_pool_bind": [vp],
         "b2d_sharded_step": [vp, c.c_int, vp, vp, vp, vp, sz, c.POINTER(c.c_int64), c.c_int, c.c_float,
@@ -248,6 +250,9 @@ class Context:
 
     def set_nvls_auto(self, enable):
         self._check(self._lib.b2d_ctx_set_nvls_auto(self._ctx, int(bool(enable))))
+
+    def set_inplace(self, enable):
+        self._check(self._lib.b2d_ctx_set_inplace(self._ctx, int(bool(enable))))
 
     def pool_bind(self, bind=True):
         """Route torch's pluggable-allocator calls (b2d_pool_alloc) to this context's arena, or unbind."""

@@ -13,6 +13,7 @@
 
 No function here has a CPU implementation: tensors must be CUDA tensors and libb2d must load.
 """
+import contextlib
 import os
 import socket
 import struct
@@ -165,6 +166,15 @@ class _Base:
     def arena_tensor(self, numel, dtype=torch.float32):
         t, _ = arena_tensor(self.ctx, numel, dtype, torch.device("cuda", self.device_index))
         return t
+
+    def owns(self, t):
+        """Does tensor ``t`` live inside this rank's symmetric arena?"""
+        base = getattr(self, "_arena_base", None)
+        if base is None:
+            p, off = self.ctx.arena_alloc(16)
+            self._arena_base = base = p - off
+            self._arena_bytes = int(self.ctx.stats()["arena_bytes"])
+        return base <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= base + self._arena_bytes
 
     def device_barrier(self, stream=None):
         st = torch.cuda.current_stream(torch.device("cuda", self.device_index)) if stream is None else stream
@@ -343,15 +353,16 @@ class LoopbackGroup:
                 os.close(fd)
             self.nvls = True
 
-    def allreduce_(self, bufs, bucket_idx=0, wire="bf16", scale=None, algo="auto"):
-        """bufs[r] is rank r's bucket; all are reduced in place. Asynchronous."""
+    def allreduce_(self, bufs, bucket_idx=0, wire="bf16", scale=None, algo="auto", wait_streams=None):
+        """bufs[r] is rank r's bucket; all are reduced in place. Asynchronous.  ``wait_streams[r]`` (default: the
+        current stream) is the stream whose work produced rank r's bucket."""
         a = self.ranks[0].ctx.plan(bufs[0].numel(), _wire(wire), _algo(algo))[0]
         phase_sets = ((_b2d.PHASE_STAGE, _b2d.PHASE_EXCHANGE, _b2d.PHASE_WRITEBACK)
                       if a in (_b2d.ALGO_STAGED, _b2d.ALGO_NVLS) and self.world > 1 else (_b2d.PHASE_ALL,))
         for ph in phase_sets:      # phase-major: no kernel ever waits for one launched after it
-            for rk, b in zip(self.ranks, bufs):
-                rk.allreduce_(b, bucket_idx, wire, scale, algo,
-                              wait_stream=torch.cuda.current_stream(b.device), comm_stream=rk.stream, phases=ph)
+            for r, (rk, b) in enumerate(zip(self.ranks, bufs)):
+                ws = torch.cuda.current_stream(b.device) if wait_streams is None else wait_streams[r]
+                rk.allreduce_(b, bucket_idx, wire, scale, algo, wait_stream=ws, comm_stream=rk.stream, phases=ph)
         return bufs
 
     def sharded_step_(self, grads, params, exp_avg, exp_avg_sq, shard_off, **kw):
@@ -385,6 +396,21 @@ class LoopbackGroup:
         self.ranks = []
 
 
+def _pg_timeout_ms(group=None):
+    """Timeout of the control-plane process group in ms (None: keep the library default of 10 minutes)."""
+    try:
+        pg = group if group is not None else dist.distributed_c10d._get_default_group()
+        t = dist.distributed_c10d._get_default_timeout(dist.get_backend(pg)) if not hasattr(pg, "options") else None
+        opt = getattr(pg, "options", None)
+        to = getattr(opt, "_timeout", None) if opt is not None else t
+        if to is None:
+            to = t
+        ms = int(to.total_seconds() * 1000)
+        return max(ms, 60_000)
+    except Exception:
+        return None
+
+
 # ---- the DDP communication hook -----------------------------------------------------------
 class B200HookState:
     """State object handed to ``DistributedDataParallel.register_comm_hook``.
@@ -396,9 +422,9 @@ class B200HookState:
     pickled to every actor (ray_launcher.py:240-245) and must not hold CUDA handles before that.
     """
 
-    def __init__(self, wire="bf16", algo="auto", process_group=None, total_grad_elems=None,
+    def __init__(self, wire="fp32", algo="auto", process_group=None, total_grad_elems=None,
                  arena_bytes=None, mem="ipc", timing=False, max_ctas=None, one_shot_max_bytes=None,
-                 nvls="auto", stream_priority=-1):
+                 nvls="auto", stream_priority=-1, timeout_ms=None, chunk_bytes=None, exch_ctas=None):
         self.wire, self.algo = wire, algo
         self.process_group = process_group
         self.total_grad_elems = total_grad_elems
@@ -406,10 +432,13 @@ class B200HookState:
         self.mem, self.timing, self.max_ctas, self.nvls = mem, timing, max_ctas, nvls
         self.one_shot_max_bytes = one_shot_max_bytes
         self.stream_priority = stream_priority
+        self.timeout_ms, self.chunk_bytes, self.exch_ctas = timeout_ms, chunk_bytes, exch_ctas
         self.comm = None
         self.stream = None
         self.calls = 0
         self.seen = {}   # bucket index -> elements, as last seen (introspection for benchmarks/tests)
+        self.in_arena = {}  # bucket index -> does the Reducer's bucket storage live in the symmetric arena?
+        self._pool = self._pool_alloc = None
 
     def ensure(self, device):
         if self.comm is not None:
@@ -421,15 +450,52 @@ class B200HookState:
             if self.total_grad_elems is None:
                 raise ValueError("B200HookState needs total_grad_elems or arena_bytes")
             nbytes = arena_bytes_for(self.total_grad_elems)
+        timeout_ms = self.timeout_ms
+        if timeout_ms is None:
+            # the watchdog follows the process group's own timeout (minutes), like torch's NCCL collectives
+            timeout_ms = _pg_timeout_ms(self.process_group)
         self.comm = Communicator(rank, world, device.index, nbytes, group=self.process_group, mem=self.mem,
                                  timing=self.timing, nvls=self.nvls, max_ctas=self.max_ctas,
-                                 one_shot_max_bytes=self.one_shot_max_bytes)
+                                 one_shot_max_bytes=self.one_shot_max_bytes, timeout_ms=timeout_ms,
+                                 chunk_bytes=self.chunk_bytes, exch_ctas=self.exch_ctas)
         # a high-priority side stream: the comm kernel's few CTAs get SMs as soon as backward frees any
         self.stream = torch.cuda.Stream(device=device, priority=self.stream_priority)
 
+    # ---- f-1: the arena as the Reducer's bucket storage ---------------------------------------------------
+    @contextlib.contextmanager
+    def allocate_in_arena(self):
+        """Everything THIS thread allocates on the communicator's device inside the block comes out of the symmetric
+        arena (torch.cuda.MemPool over b2d_pool_alloc).  Wrapped around DistributedDataParallel(...) and around
+        Reducer._rebuild_buckets() it makes the flat bucket tensors (reducer.hpp:347-406) peer-addressable, so the
+        fp32 exchange runs in place.  Every rank must allocate the same sizes in the same order."""
+        if self._pool is None:
+            self._pool_alloc = torch.cuda.memory.CUDAPluggableAllocator(_b2d.lib_path(), "b2d_pool_alloc", "b2d_pool_free")
+            self._pool = torch.cuda.MemPool(self._pool_alloc.allocator(), use_on_oom=False, no_split=True)
+        self.comm.ctx.pool_bind(True)
+        try:
+            with torch.cuda.use_mem_pool(self._pool, device=self.comm.device_index):
+                yield
+        finally:
+            self.comm.ctx.pool_bind(False)
+
+    def verify_symmetric_buckets(self):
+        """Collective, host side: in-place exchange is only valid when every rank's pool allocations landed at the
+        same arena offsets.  Compares a digest of (offset, size) over the control plane; on any mismatch the
+        in-place path is switched off everywhere (buckets are then staged like any other tensor)."""
+        st = self.comm.stats()
+        mine = (int(st["pool_allocs"]), int(st["pool_digest"]))
+        if self.comm.world > 1 and dist.is_initialized():
+            allv = [None] * self.comm.world
+            dist.all_gather_object(allv, mine, group=self.process_group)
+        else:
+            allv = [mine]
+        ok = len(set(allv)) == 1
+        self.comm.ctx.set_inplace(ok)
+        return ok
+
     def __getstate__(self):
         d = dict(self.__dict__)
-        d["comm"], d["stream"] = None, None
+        d["comm"], d["stream"], d["_pool"], d["_pool_alloc"] = None, None, None, None
         return d
 
     def close(self):
@@ -455,6 +521,7 @@ def b200_allreduce_hook(state: B200HookState, bucket: dist.GradBucket) -> torch.
                     wait_stream=cur, comm_stream=state.stream)
     state.calls += 1
     state.seen[bucket.index()] = buf.numel()
+    state.in_arena[bucket.index()] = comm.owns(buf)
     fut = torch.futures.Future(devices=[buf.device])
     with torch.cuda.stream(state.stream):
         fut.set_result(buf)

@@ -204,6 +204,8 @@ struct b2d_ctx {
   size_t chunk_bytes = 32u << 20;        // wire bytes per pipeline chunk
   int exch_ctas = 32;                    // CTAs of the exchange kernel (the only one that waits for peers)
   int nvls_auto = 1;                     // AUTO may pick the in-switch reduction when a multicast object is bound
+  int inplace = 1;                       // fp32 buckets that live in the arena are exchanged where they are
+  uint64_t pool_allocs = 0, pool_digest = 1469598103934665603ull;   // FNV-1a over (offset, size) of pool allocations
   uint64_t exch_launches = 0, exch_timed = 0;
   double exch_ms = 0.0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> exch_pending;
@@ -677,7 +679,7 @@ int launch_staged(b2d_ctx* ctx, int key, float* grad, size_t n, int wire, float 
   const size_t epp = bf16 ? 8 : 4;
   const size_t npacks = (n + epp - 1) / epp;
   const unsigned char* g8 = reinterpret_cast<const unsigned char*>(grad);
-  const bool inplace = !bf16 && g8 >= ctx->arena + kSignalBytes && g8 + npacks * 16 <= ctx->arena + ctx->arena_bytes;
+  const bool inplace = ctx->inplace && !bf16 && g8 >= ctx->arena + kSignalBytes && g8 + npacks * 16 <= ctx->arena + ctx->arena_bytes;
   const size_t cp = staged_chunk_packs(ctx);
   const int nchunks = static_cast<int>((npacks + cp - 1) / cp);
 
@@ -1157,6 +1159,11 @@ int b2d_ctx_set_exch_ctas(b2d_ctx* ctx, int ctas) {
   ctx->exch_ctas = ctas;
   return B2D_OK;
 }
+int b2d_ctx_set_inplace(b2d_ctx* ctx, int enable) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  ctx->inplace = enable ? 1 : 0;
+  return B2D_OK;
+}
 int b2d_ctx_set_nvls_auto(b2d_ctx* ctx, int enable) {
   if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
   ctx->nvls_auto = enable ? 1 : 0;
@@ -1500,7 +1507,14 @@ void* b2d_pool_alloc(size_t size, int device, void* stream) {
   { std::lock_guard<std::mutex> lk(g_pool_mu); ctx = g_pool_ctx; }
   if (ctx == nullptr || ctx->device != device) return nullptr;
   void* p = nullptr;
-  if (b2d_arena_alloc(ctx, size, &p, nullptr) != B2D_OK) return nullptr;
+  size_t off = 0;
+  if (b2d_arena_alloc(ctx, size, &p, &off) != B2D_OK) return nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->pool_allocs += 1;
+    for (uint64_t v : {static_cast<uint64_t>(off), static_cast<uint64_t>(size)})
+      for (int i = 0; i < 8; ++i) { ctx->pool_digest ^= (v >> (8 * i)) & 0xffu; ctx->pool_digest *= 1099511628211ull; }
+  }
   return p;
 }
 
@@ -1520,6 +1534,7 @@ int b2d_ctx_stats(b2d_ctx* ctx, b2d_stats* out) {
   }
   memset(out, 0, sizeof(*out));
   out->exch_launches = ctx->exch_launches; out->exch_timed = ctx->exch_timed; out->exch_ms = ctx->exch_ms;
+  out->pool_allocs = ctx->pool_allocs; out->pool_digest = ctx->pool_digest;
   out->launches = ctx->launches;
   out->timed_launches = ctx->timed_launches;
   out->timed_ms = ctx->timed_ms;

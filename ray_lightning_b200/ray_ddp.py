@@ -9,10 +9,17 @@ the Reducer finishes goes to one fused sm_100a kernel instead of cast + div + nc
 copy.  New knobs ride in as keyword arguments prefixed ``b200_`` and never reach
 ``DistributedDataParallel``:
 
-    b200_wire="bf16"|"fp32"   arithmetic contract (bf16_compress_hook | default fp32 allreduce)
-    b200_algo="auto"|"one_shot"|"two_shot"|"nvls"
+    b200_wire="fp32"|"bf16"   arithmetic contract.  Default "fp32": DDP's default divide + fp32 SUM allreduce, what the
+                              reference computes when no comm hook is given.  "bf16" is torch's ``bf16_compress_hook``
+                              (bf16 on the wire, fp32 accumulate); passing ``ddp_comm_hook=default_hooks.
+                              bf16_compress_hook`` — the reference's own way to ask for it — selects it too.
+    b200_algo="auto"|"one_shot"|"two_shot"|"staged"|"nvls"
     b200_mem="vmm"|"ipc"      how arenas are shared between the worker processes
-    b200_max_ctas, b200_one_shot_max_bytes, b200_timing, b200_nvls, b200_enable=True
+    b200_timeout_ms           peer watchdog (default: the process group's timeout; 0 = never trap)
+    b200_max_ctas, b200_one_shot_max_bytes, b200_chunk_bytes, b200_exch_ctas, b200_timing, b200_nvls,
+    b200_arena_buckets=True   (with gradient_as_bucket_view=True and the fp32 wire) let DDP's flat bucket tensors live
+                              in the symmetric arena so that buckets are exchanged in place — no stage-in copy
+    b200_enable=True
 
 There is no CPU implementation of that hook: with ``use_gpu=False`` the strategy is the
 reference's own CPU configuration (torch DDP over gloo), and with ``use_gpu=True`` a missing
@@ -27,8 +34,17 @@ import torch
 from ._compat import DDPSpawnStrategy, rank_zero_info, rank_zero_only, ray, reset_seed
 from .launchers.ray_launcher import RayLauncher
 
-_B200_DEFAULTS = dict(enable=True, wire="bf16", algo="auto", mem="vmm", max_ctas=None, one_shot_max_bytes=None,
-                      timing=False, nvls="auto", arena_bytes=None)
+_B200_DEFAULTS = dict(enable=True, wire="fp32", algo="auto", mem="vmm", max_ctas=None, one_shot_max_bytes=None,
+                      timing=False, nvls="auto", arena_bytes=None, timeout_ms=None, chunk_bytes=None, exch_ctas=None,
+                      arena_buckets=True)
+
+
+def _is_torch_bf16_hook(hook) -> bool:
+    try:
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        return hook is default_hooks.bf16_compress_hook
+    except Exception:  # pragma: no cover
+        return False
 
 
 def _split_b200_kwargs(kwargs: Dict[str, Any]) -> Dict[str, Any]:
@@ -83,6 +99,11 @@ class RayStrategy(DDPSpawnStrategy):
         self.global_to_local = None
 
         self._b200 = _split_b200_kwargs(ddp_kwargs)
+        if self.use_gpu and self._b200["enable"] and _is_torch_bf16_hook(ddp_kwargs.get("ddp_comm_hook")) \
+                and ddp_kwargs.get("ddp_comm_state") is None and ddp_kwargs.get("ddp_comm_wrapper") is None:
+            # the reference's way to ask for bf16 gradient compression: same arithmetic contract, fused kernel
+            ddp_kwargs.pop("ddp_comm_hook")
+            self._b200["wire"] = "bf16"
         if self.use_gpu and self._b200["enable"] and ddp_kwargs.get("ddp_comm_hook") is None:
             # Installed through PL's own ddp_comm_hook seam.  The state object holds no CUDA handle
             # yet (this strategy is pickled to every actor, reference ray_launcher.py:240-245).
@@ -90,7 +111,8 @@ class RayStrategy(DDPSpawnStrategy):
             o = self._b200
             ddp_kwargs["ddp_comm_state"] = B200HookState(
                 wire=o["wire"], algo=o["algo"], mem=o["mem"], timing=o["timing"], max_ctas=o["max_ctas"],
-                one_shot_max_bytes=o["one_shot_max_bytes"], nvls=o["nvls"], arena_bytes=o["arena_bytes"])
+                one_shot_max_bytes=o["one_shot_max_bytes"], nvls=o["nvls"], arena_bytes=o["arena_bytes"],
+                timeout_ms=o["timeout_ms"], chunk_bytes=o["chunk_bytes"], exch_ctas=o["exch_ctas"])
             ddp_kwargs["ddp_comm_hook"] = b200_allreduce_hook
 
         super().__init__(accelerator="_gpu" if use_gpu else "cpu", parallel_devices=[], cluster_environment=None,
@@ -134,6 +156,37 @@ class RayStrategy(DDPSpawnStrategy):
                                              init_method="env://", **kw)
         rank_zero_info("distributed_backend=%s: all %d processes registered" % (backend, self.world_size))
 
+    def configure_ddp(self) -> None:
+        """DDP construction (reference :112-116 via PL), with DDP's flat bucket tensors placed in libb2d's symmetric
+        arena when the fp32 wire is used: the hook then exchanges every bucket where it lies."""
+        st = self.b200_state
+        self.b200_arena_buckets_active = False
+        self._b200_rebuilt = False
+        self._b200_steps = 0
+        if (st is None or not self._b200["arena_buckets"] or st.wire != "fp32" or self.root_device.type != "cuda"
+                or self.world_size < 2 or self._ddp_comm_wrapper is not None):
+            return super().configure_ddp()
+        if st.total_grad_elems is None:
+            st.total_grad_elems = sum(p.numel() for p in self.model.parameters() if p.requires_grad)
+        st.ensure(self.root_device)          # collective: every worker is here
+        with st.allocate_in_arena():
+            super().configure_ddp()
+        self.b200_arena_buckets_active = st.verify_symmetric_buckets()
+
+    def training_step(self, *args):
+        st = self.b200_state
+        if getattr(self, "b200_arena_buckets_active", False) and not self._b200_rebuilt:
+            if self._b200_steps >= 1 and torch.is_grad_enabled():
+                # DDP lays its buckets out anew once, in the forward of the second iteration (reducer.hpp:125-151,
+                # distributed.py `_pre_forward`).  Do it here, with the arena as the allocator; DDP's own call is
+                # then a no-op.
+                with st.allocate_in_arena():
+                    self.model.reducer._rebuild_buckets()
+                self._b200_rebuilt = True
+                self.b200_arena_buckets_active = st.verify_symmetric_buckets()
+            self._b200_steps += 1
+        return super().training_step(*args)
+
     def _register_ddp_hooks(self) -> None:
         """Size the symmetric arena from the wrapped module, then let the base class register the hook."""
         state = getattr(self, "_ddp_comm_state", None)
@@ -153,9 +206,11 @@ class RayStrategy(DDPSpawnStrategy):
     def teardown_worker(self) -> None:
         """Worker: release the communicator before the process group goes away."""
         st = self.b200_state
+        self.model = None          # the Reducer's arena-backed buckets go before the arena does
         if st is not None:
+            import gc
+            gc.collect()
             st.close()
-        self.model = None
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             torch.distributed.destroy_process_group()
 

@@ -77,4 +77,4 @@ def test_header_is_plain_c_and_usable_from_c(tmp_path):
                     os.path.join(ROOT, "examples_c", "b2d_probe.c"), "-o", exe, "-ldl"], check=True)
     out = subprocess.run([exe, _b2d.lib_path()], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stderr
-    assert "libb2d version 100" in out.stdout
+    assert "libb2d version 110" in out.stdout

@@ -1,4 +1,4 @@
-"""Parity of the CUDA allreduce path (K0/K1/K2) against the oracle, through the C ABI.
+"""Parity of the CUDA allreduce path (K0/K1/K2 and the staged exchange K7-K10) against the oracle, through the C ABI.
 
 Every test drives libb2d exactly as the DDP hook does (b2d_allreduce_bucket on flat fp32 buckets).
 Multi-rank cases run W "loopback" ranks on the one GPU of the test box: separate contexts, arenas,
@@ -90,12 +90,12 @@ def test_wire_value_matches_torch_cuda_division(world):
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("wire", ["bf16", "fp32"])
-@pytest.mark.parametrize("algo", ["one_shot", "two_shot"])
+@pytest.mark.parametrize("algo", ["one_shot", "two_shot", "staged"])
 def test_allreduce_bit_exact_vs_oracle(world, wire, algo):
     for k, n in enumerate(SIZES):
         per_rank = rank_inputs(world, n, seed=k)
         want = oracle(per_rank, wire)
-        idx = 100 * k + (10 if wire == "bf16" else 20) + (1 if algo == "one_shot" else 2)
+        idx = 100 * k + (10 if wire == "bf16" else 20) + ["one_shot", "two_shot", "staged"].index(algo) + 1
         bufs = run(world, per_rank, wire, algo, idx)
         for r in range(world):
             assert same_bits(bufs[r], want), (world, wire, algo, n, r)
@@ -137,15 +137,62 @@ def test_tma_back_to_back_steps(world):
 
 
 @pytest.mark.parametrize("world", [2, 8])
-def test_auto_picks_one_shot_then_two_shot(world):
+def test_auto_picks_one_shot_then_the_staged_exchange(world):
     from ray_lightning_b200 import _b2d
     g = group(world)
     ctx = g.ranks[0].ctx
     assert ctx.plan(1024, _b2d.WIRE_BF16)[0] == _b2d.ALGO_ONE_SHOT
-    assert ctx.plan(8 << 20, _b2d.WIRE_BF16)[0] == (_b2d.ALGO_ONE_SHOT if world == 2 else _b2d.ALGO_TWO_SHOT)
+    assert ctx.plan(8 << 20, _b2d.WIRE_BF16)[0] == _b2d.ALGO_STAGED     # no multicast object on one GPU: P2P variant
     per_rank = rank_inputs(world, 300001)
     bufs = run(world, per_rank, "bf16", "auto", 7001)
     assert same_bits(bufs[0], oracle(per_rank, "bf16"))
+    assert ctx.stats()["last_algo"] == _b2d.ALGO_STAGED
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_staged_exchange_chunk_pipeline_bit_exact(world):
+    """Several pipeline chunks per bucket (chunk = 64 KiB of wire): stage(c+1) | exchange(c) | write-back(c-1) on the
+    three internal streams, both wires, ragged tail in the last chunk, twice on the same slot."""
+    g = group(world)
+    for rk in g.ranks:
+        rk.ctx.set_chunk_bytes(64 << 10)
+    try:
+        for wire in ("bf16", "fp32"):
+            for k, n in enumerate([(1 << 20) + 5, 300007]):
+                for rep in range(2):
+                    per_rank = rank_inputs(world, n, seed=600 + 10 * k + rep)
+                    bufs = run(world, per_rank, wire, "staged", 7100 + k + 10 * (wire == "bf16"))
+                    want = oracle(per_rank, wire)
+                    for r in range(world):
+                        assert same_bits(bufs[r], want), (world, wire, n, rep, r)
+    finally:
+        for rk in g.ranks:
+            rk.ctx.set_chunk_bytes(32 << 20)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_fp32_buckets_that_live_in_the_arena_are_exchanged_in_place(world):
+    """a bucket whose storage is arena memory needs no stage and no write-back; same bits as the
+    staged path, ragged last pack included, bytes past the end untouched."""
+    g = group(world)
+    for k, n in enumerate([1, 6, 4099, 300001, (1 << 20) + 3]):
+        per_rank = rank_inputs(world, n, seed=700 + k)
+        bufs = []
+        for rk, t in zip(g.ranks, per_rank):
+            a = rk.arena_tensor(n + 4)
+            a.fill_(777.0)
+            a[:n].copy_(t)
+            bufs.append(a)
+        torch.cuda.synchronize()
+        before = g.ranks[0].ctx.stats()["launches"]
+        g.allreduce_([b[:n] for b in bufs], bucket_idx=7200 + k, wire="fp32", algo="staged")
+        g.synchronize()
+        # in place: arrive + exchange + wait per chunk — no stage / unstage kernels
+        assert g.ranks[0].ctx.stats()["launches"] - before == 3
+        want = oracle(per_rank, "fp32")
+        for r in range(world):
+            assert same_bits(bufs[r][:n], want), (world, n, r)
+            assert float(bufs[r][n]) == 777.0 and float(bufs[r][n + 3]) == 777.0
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -154,8 +201,8 @@ def test_special_values_propagate(world):
                             1.00390625, 1.005859375, 2.0 ** -126, 2.0 ** -133, 65504.0, -1.0])
     per_rank = [torch.cat([special.roll(r), rank_inputs(world, 50)[r]]) for r in range(world)]
     for wire in ("bf16", "fp32"):
-        for algo in ("one_shot", "two_shot"):
-            bufs = run(world, per_rank, wire, algo, 8000 + (wire == "bf16") * 2 + (algo == "one_shot"))
+        for ai, algo in enumerate(("one_shot", "two_shot", "staged")):
+            bufs = run(world, per_rank, wire, algo, 8000 + (wire == "bf16") * 3 + ai)
             want = oracle(per_rank, wire)
             got = bufs[0].cpu()
             assert torch.equal(torch.isnan(got), torch.isnan(want))
@@ -163,7 +210,8 @@ def test_special_values_propagate(world):
             assert same_bits(got[ok], want[ok])
 
 
-@pytest.mark.parametrize("world,algo", [(2, "two_shot"), (4, "two_shot"), (8, "two_shot"), (4, "one_shot")])
+@pytest.mark.parametrize("world,algo", [(2, "two_shot"), (4, "two_shot"), (8, "two_shot"), (4, "one_shot"),
+                                        (2, "staged"), (4, "staged"), (8, "staged")])
 def test_back_to_back_steps_without_host_sync(world, algo):
     """Five consecutive steps on the same bucket slot, launched back to back: exercises the double
     buffering that replaces a trailing barrier."""
@@ -173,7 +221,7 @@ def test_back_to_back_steps_without_host_sync(world, algo):
     bufs = [[t.cuda() for t in per_rank] for per_rank in steps]
     torch.cuda.synchronize()
     for s in range(5):
-        g.allreduce_(bufs[s], bucket_idx=9000 + world, wire="bf16", algo=algo)
+        g.allreduce_(bufs[s], bucket_idx=9000 + world + 10 * (algo == "staged"), wire="bf16", algo=algo)
     g.synchronize()
     for s in range(5):
         want = oracle(steps[s], "bf16")
@@ -217,6 +265,9 @@ def test_full_size_resnet50_bucket_properties(world):
     want = oracle(per_rank, "bf16")
     for r in range(world):
         assert same_bits(bufs[r], want)
+    staged = run(world, per_rank, "bf16", "staged", 9901)
+    for r in range(world):
+        assert same_bits(staged[r], want)
     out = bufs[0].clone()
     # (1) results are bf16-representable: rounding again changes nothing
     assert same_bits(out, out.to(torch.bfloat16).float())
@@ -232,7 +283,7 @@ def test_full_size_resnet50_bucket_properties(world):
 
 
 @pytest.mark.parametrize("world", [4, 8])
-@pytest.mark.parametrize("algo", ["one_shot", "two_shot", "two_shot_tma"])
+@pytest.mark.parametrize("algo", ["one_shot", "two_shot", "two_shot_tma", "staged"])
 def test_allreduce_with_skewed_ranks(world, algo):
     """A rotating straggler (about 1 ms of device sleep before its kernel) over 8 back-to-back steps on the
     same slot: barriers, arrival-order gather and double buffering under skew."""
@@ -241,12 +292,119 @@ def test_allreduce_with_skewed_ranks(world, algo):
     steps = [rank_inputs(world, n, seed=200 + s) for s in range(8)]
     bufs = [[t.cuda() for t in per_rank] for per_rank in steps]
     torch.cuda.synchronize()
+    producers = [torch.cuda.Stream() for _ in range(world)]   # the staged algorithms consume in wait-stream order
     for s in range(8):
-        with torch.cuda.stream(g.ranks[(3 * s) % world].stream):
+        slow = (3 * s) % world
+        with torch.cuda.stream(g.ranks[slow].stream):
             torch.cuda._sleep(2_000_000)
-        g.allreduce_(bufs[s], bucket_idx=9950 + ["one_shot", "two_shot", "two_shot_tma"].index(algo), wire="bf16", algo=algo)
+        with torch.cuda.stream(producers[slow]):
+            torch.cuda._sleep(2_000_000)
+        g.allreduce_(bufs[s], bucket_idx=9950 + ["one_shot", "two_shot", "two_shot_tma", "staged"].index(algo), wire="bf16",
+                     algo=algo, wait_streams=producers if algo == "staged" else None)
     g.synchronize()
     for s in range(8):
         want = oracle(steps[s], "bf16")
         for r in range(world):
             assert same_bits(bufs[s][r], want), (s, r)
+
+
+# ---- NVLS: needs an NVSwitch box with at least two GPUs -------------------------------------------------------
+def _nvls_group():
+    from ray_lightning_b200 import _b2d
+    from ray_lightning_b200.comm import LoopbackGroup
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("NVLS needs at least two GPUs behind an NVSwitch")
+    world = 8 if nd >= 8 else (4 if nd >= 4 else 2)
+    if "nvls" not in _groups:
+        try:
+            _groups["nvls"] = LoopbackGroup(world, devices=list(range(world)), arena_bytes=256 << 20, timeout_ms=20000,
+                                            mem="vmm", nvls=True)
+        except _b2d.B2DError as e:
+            pytest.skip("multicast not available on this box: %s" % e)
+    return _groups["nvls"]
+
+
+def _nvls_run(g, per_rank, wire, algo, idx):
+    bufs = [t.to("cuda:%d" % rk.device_index) for rk, t in zip(g.ranks, per_rank)]
+    for rk in g.ranks:
+        torch.cuda.synchronize(rk.device_index)
+    g.allreduce_(bufs, bucket_idx=idx, wire=wire, algo=algo)
+    g.synchronize()
+    return bufs
+
+
+@pytest.mark.parametrize("algo", ["nvls", "nvls_fused"])
+def test_nvls_matches_the_exact_sum_to_one_rounding(algo):
+    """The in-switch reduction (multimem.ld_reduce / multimem.st) on real NVLink.  Contract: every rank
+    receives the SAME bits; fp32 wire within rtol 1e-6 of the rank-ordered oracle (north star: 1e-3 / 1e-5); bf16 wire:
+    the result is one of the two bf16 neighbours of the exact (fp64) sum of the wire values — one rounding, as the oracle."""
+    g = _nvls_group()
+    world = g.world
+    for k, n in enumerate([8, 4099, 300007, (1 << 20) + 5, 7874560]):
+        per_rank = rank_inputs(world, n, seed=800 + k)
+        fp = _nvls_run(g, per_rank, "fp32", algo, 7300 + k)
+        want = oracle(per_rank, "fp32")
+        for r in range(world):
+            assert same_bits(fp[r], fp[0]), (n, r)
+        torch.testing.assert_close(fp[0].cpu(), want, rtol=1e-5, atol=1e-8)
+        bf = _nvls_run(g, per_rank, "bf16", algo, 7400 + k)
+        for r in range(world):
+            assert same_bits(bf[r], bf[0]), (n, r)
+        scale = float(np.float32(1.0) / np.float32(world))
+        exact = sum(ddp_oracle.wire_bf16(t, scale).double() for t in per_rank)
+        got = bf[0].cpu().double()
+        ulp = torch.maximum(got.abs(), exact.abs()) * 2.0 ** -7     # spacing of bf16 at that magnitude (upper bound)
+        assert bool(((got - exact).abs() <= ulp + 1e-30).all())
+        assert same_bits(bf[0], bf[0].to(torch.bfloat16).float())
+        # and it is not further from the exact sum than the oracle's own rank-ordered result by more than one step
+        mine = (got - exact).abs().max()
+        ref = (oracle(per_rank, "bf16").double() - exact).abs().max()
+        assert float(mine) <= 2.0 * float(ref) + 1e-12
+
+
+def test_auto_prefers_nvls_from_four_ranks_up():
+    from ray_lightning_b200 import _b2d
+    g = _nvls_group()
+    a = g.ranks[0].ctx.plan(8 << 20, _b2d.WIRE_BF16)[0]
+    assert a == (_b2d.ALGO_NVLS if g.world >= 4 else _b2d.ALGO_STAGED)
+    for rk in g.ranks:
+        rk.ctx.set_nvls_auto(False)
+    try:
+        assert g.ranks[0].ctx.plan(8 << 20, _b2d.WIRE_BF16)[0] == _b2d.ALGO_STAGED
+    finally:
+        for rk in g.ranks:
+            rk.ctx.set_nvls_auto(True)
+
+
+def test_staged_p2p_across_real_gpus_bit_exact():
+    """The P2P variant over NVLink (peer loads + peer stores between distinct devices), bit-exact like on one GPU."""
+    g = _nvls_group()
+    for k, n in enumerate([9, 300007, 7874560]):
+        per_rank = rank_inputs(g.world, n, seed=850 + k)
+        for wire in ("bf16", "fp32"):
+            bufs = _nvls_run(g, per_rank, wire, "staged", 7500 + 2 * k + (wire == "bf16"))
+            want = oracle(per_rank, wire)
+            for r in range(g.world):
+                assert same_bits(bufs[r], want), (n, wire, r)
+
+
+def test_nvls_in_place_fp32():
+    g = _nvls_group()
+    n = 300001
+    per_rank = rank_inputs(g.world, n, seed=870)
+    bufs = []
+    for rk, t in zip(g.ranks, per_rank):
+        a = rk.arena_tensor(n + 4)
+        a.fill_(777.0)
+        a[:n].copy_(t.to(a.device))
+        bufs.append(a)
+    for rk in g.ranks:
+        torch.cuda.synchronize(rk.device_index)
+    g.allreduce_([b[:n] for b in bufs], bucket_idx=7600, wire="fp32", algo="nvls")
+    g.synchronize()
+    want = oracle(per_rank, "fp32")
+    for r in range(g.world):
+        torch.testing.assert_close(bufs[r][:n].cpu(), want, rtol=1e-5, atol=1e-8)
+        assert same_bits(bufs[r][:n], bufs[0][:n])
+        assert float(bufs[r][n]) == 777.0

@@ -35,15 +35,21 @@ def _worker(rank, world, port, mem, ret):
             per_rank = [torch.randn(n, generator=torch.Generator().manual_seed(77 + r + 10 * k)) * 0.05
                         for r in range(world)]
             for wire in ("bf16", "fp32"):
-                for ai, algo in enumerate(("one_shot", "two_shot", "two_shot_tma")):
+                for ai, algo in enumerate(("one_shot", "two_shot", "two_shot_tma", "staged")):
                     if algo == "two_shot_tma" and wire == "fp32":
                         continue
                     buf = per_rank[rank].cuda()
-                    comm.allreduce_(buf, bucket_idx=k * 10 + (wire == "bf16") * 3 + ai, wire=wire, algo=algo)
+                    comm.allreduce_(buf, bucket_idx=k * 10 + (wire == "bf16") * 4 + ai, wire=wire, algo=algo)
                     torch.cuda.synchronize()
                     fn = ddp_oracle.allreduce_bf16_wire if wire == "bf16" else ddp_oracle.allreduce_fp32_wire
                     want = fn(per_rank)
                     ok = ok and torch.equal(buf.cpu().view(torch.int32), want.view(torch.int32))
+                if comm.nvls:   # real NVSwitch multicast between the worker processes: tolerance contract
+                    buf = per_rank[rank].cuda()
+                    comm.allreduce_(buf, bucket_idx=900 + k * 2 + (wire == "bf16"), wire=wire, algo="nvls")
+                    torch.cuda.synchronize()
+                    fn = ddp_oracle.allreduce_bf16_wire if wire == "bf16" else ddp_oracle.allreduce_fp32_wire
+                    ok = ok and torch.allclose(buf.cpu(), fn(per_rank), rtol=1e-2 if wire == "bf16" else 1e-5, atol=1e-5)
         st = comm.stats()
         ret[rank] = {"ok": ok, "nvls": comm.nvls, "launches": st["launches"], "mem_kind": st["mem_kind"]}
     finally:
@@ -62,7 +68,8 @@ def test_worker_processes_share_arenas(world, mem):
     assert sorted(ret.keys()) == list(range(world))
     for r in range(world):
         assert ret[r]["ok"], (r, dict(ret[r]))
-        assert ret[r]["launches"] == 15
+        # 3 sizes x (5 single-kernel calls + staged bf16 + staged fp32 = 2 x (stage, exchange, wait, write-back)) [+ NVLS]
+        assert ret[r]["launches"] == 3 * (5 + 8) + (3 * 8 if ret[r]["nvls"] else 0)
         assert ret[r]["mem_kind"] == (1 if mem == "vmm" else 0)
 
 

@@ -1,4 +1,4 @@
-"""Exhaustive interleaving check of the inter-GPU protocol of the two-shot kernel.
+"""Exhaustive interleaving check of the inter-GPU protocols (two-shot kernel, sharded step, staged exchange).
 
 The kernels synchronise same-index blocks of the W ranks with epoch flags and avoid a trailing barrier by
 alternating two staging halves per bucket slot.  That argument is easy to get subtly wrong, and a GPU test
@@ -183,69 +183,55 @@ def test_the_sharded_model_catches_a_missing_gather_barrier():
     assert bad is not None and "parameter version" in bad
 
 
-def explore_pipelined(world, steps, chunks, halves=2, kernel_join=True, max_states=4_000_000):
-    """Role-decoupled chunk pipeline (the K2P design): per rank three concurrent roles coupled only by
-    monotone per-role counters — S stages chunk c and publishes cntA = base+c+1; R waits cntA of ALL ranks,
-    reduces chunk c of its slice in place, publishes cntB; G waits cntB of all ranks and gathers chunk c.
-    A kernel call ends when all three roles of the rank are done (join); consecutive calls alternate halves.
-    Checked: every read sees (kind, step) it expects; no deadlock."""
-    # per (rank, role) program for step k: list of ops
-    def prog_S(k):
-        return [x for c in range(chunks) for x in (("stage", (k, c)), ("pubA", k * chunks + c + 1))]
-
-    def prog_R(k):
-        return [x for c in range(chunks) for x in (("waitA", k * chunks + c + 1), ("reduce", (k, c)), ("pubB", k * chunks + c + 1))]
-
-    def prog_G(k):
-        return [x for c in range(chunks) for x in (("waitB", k * chunks + c + 1), ("gather", (k, c)))]
-
-    progs = {"S": prog_S, "R": prog_R, "G": prog_G}
-    roles = ("S", "R", "G")
-    # state: step[rank], pc[rank][role], mem[rank][half][chunk][slice]=(kind,step), cntA[rank][src], cntB[rank][src]
+def explore_staged(world, steps, chunks, halves=2, reuse_edge=True, max_states=4_000_000):
+    """The staged exchange (csrc/b2d_staged.cuh): per rank three concurrent in-order streams coupled by two
+    monotone flags per source rank and ONE local ordering edge —
+        S  for every (step k, chunk c): [local: U has finished step k - halves]  stage chunk c into half k % halves;
+           publish staged = idx
+        X  wait staged[p] >= idx for ALL p (own included); read chunk c / own slice of every rank (must be the staged
+           values of step k); PUSH the reduced slice into every rank's half; publish published = idx
+        U  wait published[p] >= idx for ALL p; read the whole chunk from the OWN half (must be step k's reduced values)
+    No kernel ever waits after it has published, and nothing else orders the streams of a rank (the event edges
+    S->X and X->U of b2d.cu are implied by the flags, so the model is strictly more permissive than the code).
+    Checked: every read sees the (kind, step) it expects; no reachable state is a deadlock."""
+    idx = lambda k, c: k * chunks + c + 1
+    prog = {
+        "S": [x for k in range(steps) for c in range(chunks) for x in (("stage", (k, c)), ("pubA", idx(k, c)))],
+        "X": [x for k in range(steps) for c in range(chunks) for x in (("waitA", idx(k, c)), ("exch", (k, c)), ("pubB", idx(k, c)))],
+        "U": [x for k in range(steps) for c in range(chunks) for x in (("waitB", idx(k, c)), ("unstage", (k, c)))],
+    }
+    roles = ("S", "X", "U")
     empty = (-1, -1)
     mem0 = tuple(tuple(tuple(tuple([empty] * world) for _ in range(chunks)) for _ in range(halves)) for _ in range(world))
     zero = tuple(tuple([0] * world) for _ in range(world))
-    init = (tuple([0] * world), tuple((0, 0, 0) for _ in range(world)), mem0, zero, zero)
+    init = (tuple((0, 0, 0) for _ in range(world)), mem0, zero, zero)
     seen, todo = {init}, deque([init])
-    lens = {r: len(progs[r](0)) for r in roles}
 
-    def setmem(mem, p, h, c, sl, val):
-        m = [[[list(x) for x in ch] for ch in hf] for hf in mem]
-        if sl is None:
-            m[p][h][c] = [val] * world
-        else:
-            m[p][h][c][sl] = val
+    def freeze(m):
         return tuple(tuple(tuple(tuple(x) for x in ch) for ch in hf) for hf in m)
 
+    def thaw(mem):
+        return [[[list(x) for x in ch] for ch in hf] for hf in mem]
+
     while todo:
-        stepv, pcs, mem, cntA, cntB = todo.popleft()
+        pcs, mem, cntA, cntB = todo.popleft()
         moved = False
         done_all = True
         for r in range(world):
-            k = stepv[r]
-            if k == steps:
-                continue
-            done_all = False
-            # kernel join: next step starts only when all three roles finished this one
-            if all(pcs[r][i] == lens[roles[i]] for i in range(3)):
-                nstep = stepv[:r] + (k + 1,) + stepv[r + 1:]
-                npcs = pcs[:r] + ((0, 0, 0),) + pcs[r + 1:]
-                nxt = (nstep, npcs, mem, cntA, cntB)
-                moved = True
-                if nxt not in seen:
-                    seen.add(nxt); todo.append(nxt)
-                continue
             for ri, role in enumerate(roles):
                 pc = pcs[r][ri]
-                if pc == lens[role]:
+                if pc == len(prog[role]):
                     continue
-                if not kernel_join:
-                    pass
-                op, arg = progs[role](k)[pc]
+                done_all = False
+                op, arg = prog[role][pc]
                 nmem, nA, nB = mem, cntA, cntB
                 if op == "stage":
-                    kk, c = arg
-                    nmem = setmem(mem, r, kk % halves, c, None, (0, kk))
+                    k, c = arg
+                    if reuse_edge and k >= halves and pcs[r][2] < 2 * chunks * (k - halves + 1):
+                        continue          # the half's previous write-back has not finished (reuse_ev in b2d.cu)
+                    m = thaw(mem)
+                    m[r][k % halves][c] = [(0, k)] * world
+                    nmem = freeze(m)
                 elif op == "pubA":
                     a = [list(x) for x in cntA]
                     for p in range(world):
@@ -262,35 +248,43 @@ def explore_pipelined(world, steps, chunks, halves=2, kernel_join=True, max_stat
                 elif op == "waitB":
                     if any(cntB[r][p] < arg for p in range(world)):
                         continue
-                elif op == "reduce":
-                    kk, c = arg
+                elif op == "exch":
+                    k, c = arg
                     for p in range(world):
-                        if mem[p][kk % halves][c][r] != (0, kk):
-                            return "rank %d reduces (step %d, chunk %d) but rank %d holds %r" % (r, kk, c, p, mem[p][kk % halves][c][r])
-                    nmem = setmem(mem, r, kk % halves, c, r, (1, kk))
-                elif op == "gather":
-                    kk, c = arg
+                        if mem[p][k % halves][c][r] != (0, k):
+                            return "rank %d reduces (step %d, chunk %d) but rank %d holds %r" % (r, k, c, p, mem[p][k % halves][c][r])
+                    m = thaw(mem)
                     for p in range(world):
-                        if mem[p][kk % halves][c][p] != (1, kk):
-                            return "rank %d gathers (step %d, chunk %d) but rank %d holds %r" % (r, kk, c, p, mem[p][kk % halves][c][p])
+                        m[p][k % halves][c][r] = (1, k)
+                    nmem = freeze(m)
+                elif op == "unstage":
+                    k, c = arg
+                    for sl in range(world):
+                        if mem[r][k % halves][c][sl] != (1, k):
+                            return "rank %d writes back (step %d, chunk %d) but slice %d holds %r" % (r, k, c, sl, mem[r][k % halves][c][sl])
                 moved = True
                 row = list(pcs[r]); row[ri] = pc + 1
-                nxt = (stepv, pcs[:r] + (tuple(row),) + pcs[r + 1:], nmem, nA, nB)
+                nxt = (pcs[:r] + (tuple(row),) + pcs[r + 1:], nmem, nA, nB)
                 if nxt not in seen:
                     seen.add(nxt)
                     if len(seen) > max_states:
                         raise RuntimeError("state space larger than expected")
                     todo.append(nxt)
         if not moved and not done_all:
-            return "deadlock at steps %r pcs %r" % (stepv, pcs)
+            return "deadlock at pcs %r" % (pcs,)
     return None
 
 
-@pytest.mark.parametrize("world,steps,chunks", [(2, 3, 2), (2, 2, 3), (3, 2, 2)])
-def test_role_decoupled_chunk_pipeline_is_safe(world, steps, chunks):
-    assert explore_pipelined(world, steps, chunks) is None
+@pytest.mark.parametrize("world,steps,chunks", [(2, 3, 2), (2, 4, 1), (3, 3, 1)])
+def test_staged_exchange_protocol_is_safe(world, steps, chunks):
+    assert explore_staged(world, steps, chunks) is None
 
 
-def test_pipelined_model_catches_single_buffering():
-    bad = explore_pipelined(2, 3, 2, halves=1)
+def test_staged_exchange_single_buffered_is_safe_too():
+    """With the write-back edge even ONE half is safe (consecutive uses of a slot just serialise)."""
+    assert explore_staged(2, 3, 2, halves=1) is None
+
+
+def test_staged_model_catches_a_missing_reuse_edge():
+    bad = explore_staged(2, 3, 1, reuse_edge=False)
     assert bad is not None and "holds" in bad
