@@ -133,13 +133,19 @@ class EarlyStopping(Callback):
             return
         cur = float(trainer.callback_metrics[self.monitor])
         better = self.best is None or (cur < self.best - self.min_delta if self.mode == "min" else cur > self.best + self.min_delta)
+        stop = False
         if better:
             self.best, self.wait_count = cur, 0
         else:
             self.wait_count += 1
-            if self.wait_count >= self.patience:
-                trainer.should_stop = True
-                self.stopped_epoch = trainer.current_epoch
+            stop = self.wait_count >= self.patience
+        # The monitored metric is per rank (the validation set is sharded by DistributedSampler and logged values
+        # are not reduced), so ranks may disagree; a rank that left the loop alone would strand the others in
+        # their next collective.  PL settles it with strategy.reduce_boolean_decision: stop if ANY rank wants to.
+        stop = trainer.strategy.reduce_boolean_decision(stop, all=False)
+        if stop:
+            trainer.should_stop = True
+            self.stopped_epoch = trainer.current_epoch
 
 
 class ModelCheckpoint(Callback):
@@ -157,12 +163,15 @@ class ModelCheckpoint(Callback):
 
     def on_train_epoch_end(self, trainer, pl_module):
         score = None
+        save = True
         if self.monitor is not None and self.monitor in trainer.callback_metrics:
             score = float(trainer.callback_metrics[self.monitor])
             if self.best_model_score is not None:
-                worse = score >= self.best_model_score if self.mode == "min" else score <= self.best_model_score
-                if worse:
-                    return
+                save = not (score >= self.best_model_score if self.mode == "min" else score <= self.best_model_score)
+        # saving is collective (the sharded strategy consolidates optimizer state on every rank): rank 0 decides
+        save = bool(trainer.strategy.broadcast(save, src=0))
+        if not save:
+            return
         path = self._path(trainer)
         if trainer.is_global_zero:
             old = self.best_model_path
@@ -346,6 +355,14 @@ class Strategy:
     def broadcast(self, obj, src=0):
         return obj
 
+    def reduce_boolean_decision(self, decision, all=True):
+        """PL's Strategy.reduce_boolean_decision: every rank leaves with the same answer (all / any)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return bool(decision)
+        t = torch.tensor([int(bool(decision))], device=self.root_device)
+        dist.all_reduce(t)
+        return bool(int(t) == dist.get_world_size()) if all else bool(int(t) > 0)
+
     def reduce(self, tensor, group=None, reduce_op="mean"):
         return tensor
 
@@ -436,6 +453,14 @@ class DDPSpawnStrategy(ParallelStrategy):
         box = [obj]
         dist.broadcast_object_list(box, src=src)
         return box[0]
+
+    def reduce_boolean_decision(self, decision, all=True):
+        """PL's Strategy.reduce_boolean_decision: every rank leaves with the same answer (all / any)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return bool(decision)
+        t = torch.tensor([int(bool(decision))], device=self.root_device)
+        dist.all_reduce(t)
+        return bool(int(t) == dist.get_world_size()) if all else bool(int(t) > 0)
 
     def reduce(self, tensor, group=None, reduce_op="mean"):
         if not (dist.is_available() and dist.is_initialized()) or not isinstance(tensor, torch.Tensor):

@@ -167,7 +167,8 @@ class ShardedOptimizer(torch.optim.Optimizer):
         return self.consolidated_state_dict()
 
     def load_state_dict(self, sd):
-        """Accepts the consolidated layout (any previous world size) and keeps the owned slice."""
+        """Accepts the consolidated layout (written by any previous world size) and keeps the owned slice —
+        the resume-with-fewer-workers contract of ray_lightning/tests/test_ddp_sharded.py:118-137."""
         sh = self.shards
         g = dict(sd["param_groups"][0])
         g.pop("params", None)
@@ -175,10 +176,38 @@ class ShardedOptimizer(torch.optim.Optimizer):
         st = sd.get("state", {})
         if not st:
             return
+        st = {int(k): v for k, v in st.items()}
         lo = sh.own.start
+        n_own = sh.own.stop - sh.own.start
+        mine = [(i, off, n) for i, (off, n) in enumerate(zip(sh.offsets, sh.numels)) if sh.owner[i] == self.comm.rank]
         if self.fused:
-            for i, (off, n) in enumerate(zip(sh.offsets, sh.numels)):
-                if sh.owner[i] == self.comm.rank and i in st:
+            for i, off, n in mine:
+                if i in st:
                     self.exp_avg[off - lo:off - lo + n].copy_(st[i]["exp_avg"].reshape(-1))
                     self.exp_avg_sq[off - lo:off - lo + n].copy_(st[i]["exp_avg_sq"].reshape(-1))
                     self._steps = int(st[i]["step"])
+            return
+        # any other elementwise optimizer: its state belongs to ONE flat parameter (the owned shard); every
+        # full-size per-parameter state tensor is cut to the owned range, scalars (step counts, ...) are taken as is
+        if not mine:
+            return
+        keys = set()
+        for i, _, _ in mine:
+            if i not in st:
+                raise ValueError("optimizer state for parameter %d is missing from the checkpoint" % i)
+            keys |= set(st[i].keys())
+        own_state = {}
+        dev = sh.flat_params.device
+        for key in sorted(keys):
+            first = st[mine[0][0]][key]
+            if isinstance(first, torch.Tensor) and first.numel() == mine[0][2] and first.dim() > 0:
+                flat = torch.zeros(max(n_own, 1), device=dev, dtype=torch.float32)
+                for i, off, n in mine:
+                    v = st[i][key]
+                    if not isinstance(v, torch.Tensor) or v.numel() != n:
+                        raise ValueError("optimizer state %r of parameter %d has an unexpected shape" % (key, i))
+                    flat[off - lo:off - lo + n].copy_(v.reshape(-1))
+                own_state[key] = flat[:n_own].view_as(self._own_param)
+            else:
+                own_state[key] = first.clone() if isinstance(first, torch.Tensor) else first
+        self._base.state[self._own_param] = own_state

@@ -182,6 +182,29 @@ def test_early_stop(tmpdir, ray_start_2_cpus):
     assert trained.val_epoch == patience + 1, trained.val_epoch
 
 
+def test_early_stop_with_rank_dependent_metrics(tmpdir, ray_start_2_cpus):
+    """Ranks that disagree about the monitored metric must still leave the fit loop together (PL's
+    reduce_boolean_decision): rank 1 sees a val_loss that keeps improving, rank 0 a constant one.  Without the
+    reduction rank 0 stops alone and rank 1 hangs in its next allreduce."""
+
+    class Skewed(BoringModel):
+        def validation_step(self, batch, batch_idx):
+            self.layer(batch)
+            rank = self.trainer.strategy.global_rank
+            loss = torch.tensor(1.0 if rank == 0 else 1.0 / (1.0 + self.val_epoch))
+            self.log("val_loss", loss)
+            return {"x": loss}
+
+    patience = 2
+    trainer = get_trainer(tmpdir, max_epochs=50, strategy=RayStrategy(num_workers=2, use_gpu=False),
+                          callbacks=[EarlyStopping(monitor="val_loss", patience=patience)],
+                          limit_train_batches=2, limit_val_batches=2)
+    trainer.fit(Skewed())
+    assert trainer.state.finished
+    trained = Skewed.load_from_checkpoint(trainer.checkpoint_callback.best_model_path)
+    assert trained.val_epoch == patience + 1, trained.val_epoch     # rank 0's decision, taken by both
+
+
 def test_unused_parameters(tmpdir, ray_start_2_cpus):
     """find_unused_parameters=False reaches torch DDP (reference :311-323); default is PL's True."""
 

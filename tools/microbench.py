@@ -76,106 +76,98 @@ def loopback():
         g.close()
 
 
-def sweep():
-    """Real multi-GPU sweep (one process per GPU, launched by torchrun): libb2d vs NCCL."""
+def _comm():
     import torch.distributed as dist
     from ray_lightning_b200.comm import Communicator
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    mem = os.environ.get("B2D_MEM", "vmm")
-    max_ctas = int(os.environ.get("B2D_MAX_CTAS", "128"))
-    comm = Communicator(rank, world, local, 3 << 30, mem=mem, max_ctas=max_ctas, timeout_ms=20000, nvls="auto")
-    if os.environ.get("B2D_TMA_CTAS"):
-        comm.ctx.set_tma_ctas(int(os.environ["B2D_TMA_CTAS"]))
+    env = os.environ.get
+    comm = Communicator(rank, world, local, int(env("B2D_ARENA_MB", "3072")) << 20, mem=env("B2D_MEM", "vmm"),
+                        max_ctas=int(env("B2D_MAX_CTAS", "128")), timeout_ms=20000, nvls="auto",
+                        chunk_bytes=(int(env("B2D_CHUNK_MB")) << 20) if env("B2D_CHUNK_MB") else None,
+                        exch_ctas=int(env("B2D_EXCH_CTAS")) if env("B2D_EXCH_CTAS") else None)
+    return dist, comm, rank, world
+
+
+def sweep():
+    """Real multi-GPU sweep (one process per GPU, launched by torchrun): libb2d (every algorithm) vs ncclAllReduce,
+    the reference's bf16 hook sequence and torch.ops.symm_mem.*; link probe; parity vs NCCL."""
+    from bench import allreduce_sweep, link_probe
+    dist, comm, rank, world = _comm()
     if rank == 0:
-        print(json.dumps({"bench": "sweep_setup", "world": world, "mem": mem, "nvls": comm.nvls, "max_ctas": max_ctas}), flush=True)
-    side = torch.cuda.Stream()
+        print(json.dumps({"bench": "sweep_setup", "world": world, "nvls": comm.nvls, "stats": {k: comm.stats()[k] for k in ("arena_bytes", "mc_bound")}}), flush=True)
+    link = link_probe(comm, dist, torch, world, rank)
+    if rank == 0:
+        print(json.dumps({"bench": "link_probe", **link}), flush=True)
     sizes = [64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 64 << 20, 256 << 20]  # bytes of WIRE payload (bf16)
-    iters = int(os.environ.get("B2D_ITERS", "30"))
-
-    def timed(fn, n_it):
-        for _ in range(5):
-            fn()
-        torch.cuda.synchronize()
-        dist.barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(n_it):
-            fn()
-        b.record()
-        b.synchronize()
-        t = torch.tensor([a.elapsed_time(b) / n_it], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
-
-    for wire_bytes in sizes:
-        n = wire_bytes // 2
-        buf = torch.randn(n, device="cuda") * 0.01
-        ref = buf.clone()
-        bus = 2 * (world - 1) / world * wire_bytes
-        rows = {}
-        algos = ["one_shot", "two_shot", "two_shot_tma"] + (["nvls"] if comm.nvls and os.environ.get("B2D_SKIP_NVLS") != "1" else [])
-        for algo in algos:
-            if algo == "one_shot" and wire_bytes > (16 << 20):
-                continue
-            key = sizes.index(wire_bytes) * 10 + algos.index(algo)
-            f = lambda: comm.allreduce_(buf, bucket_idx=key, wire="bf16", algo=algo)
-            rows[algo] = timed(f, iters)
-            if os.environ.get("B2D_TRACE") == "1":
-                comm.ctx.trace(True)
-                torch.cuda.synchronize(); dist.barrier()
-                f()
-                ph = comm.ctx.trace(True, read=True)
-                if rank == 0:
-                    print(json.dumps({"bench": "trace", "world": world, "wire_bytes": wire_bytes, "algo": algo,
-                                      "grid": comm.ctx.stats()["last_grid"],
-                                      "phase_us(stage,barrierA,reduce,barrierB,gather,...,span)": [round(x, 2) for x in ph]}), flush=True)
-                comm.ctx.trace(False)
-        # the reference GPU path with the bf16 hook: cast+div, ncclAllReduce(bf16), copy back
-        def nccl_bf16():
-            c = buf.to(torch.bfloat16).div_(world)
-            dist.all_reduce(c)
-            buf.copy_(c)
-        if os.environ.get("B2D_SKIP_NCCL") != "1":
-            rows["nccl_bf16_hook_seq"] = timed(nccl_bf16, iters)
-            cb = buf.to(torch.bfloat16)
-            rows["nccl_bf16_allreduce_only"] = timed(lambda: dist.all_reduce(cb), iters)
-        if os.environ.get("B2D_SKIP_FP32") != "1":
-            rows["nccl_fp32_allreduce"] = timed(lambda: dist.all_reduce(buf), iters)
-        buf.copy_(ref)
-        if rank == 0:
-            out = {"bench": "sweep", "world": world, "wire_bytes": wire_bytes, "n": n}
-            for k, ms in rows.items():
-                out[k + "_ms"] = round(ms, 4)
-                w = 4 * n if k == "nccl_fp32_allreduce" else wire_bytes
-                out[k + "_busGBps"] = round(2 * (world - 1) / world * w / ms / 1e6, 1)
-            print(json.dumps(out), flush=True)
+    rows = allreduce_sweep(comm, dist, torch, world, rank, sizes, iters=int(os.environ.get("B2D_ITERS", "30")))
+    if rank == 0:
+        for row in rows:
+            print(json.dumps({"bench": "sweep", "world": world, **row}), flush=True)
     # correctness against NCCL on the same inputs
     g = torch.randn(1 << 20, device="cuda", generator=torch.Generator("cuda").manual_seed(rank))
-    mine = g.clone()
-    comm.allreduce_(mine, bucket_idx=999, wire="fp32", algo="two_shot")
+    out = {"bench": "sweep_parity_vs_nccl"}
     theirs = g / world
     dist.all_reduce(theirs)
-    torch.cuda.synchronize()
-    ok = torch.allclose(mine, theirs, rtol=1e-3, atol=1e-5)   # north-star tolerance vs the reference's fp32 path
-    # bf16 wire: NCCL rounds every partial sum, libb2d once — compare both with the exact fp64 sum of the wire values
-    mine2 = g.clone()
-    comm.allreduce_(mine2, bucket_idx=998, wire="bf16", algo="two_shot")
     c = g.to(torch.bfloat16).div_(world)
     parts = [torch.empty_like(c) for _ in range(world)]
     dist.all_gather(parts, c)
     exact = sum(p.double() for p in parts)
     dist.all_reduce(c)
     torch.cuda.synchronize()
-    err_mine = float((mine2.double() - exact).abs().max())
-    err_nccl = float((c.double() - exact).abs().max())
+    out["bf16_max_err_vs_exact_nccl"] = float((c.double() - exact).abs().max())
+    for ai, algo in enumerate(["two_shot", "staged"] + (["nvls"] if comm.nvls else [])):
+        mine = g.clone()
+        comm.allreduce_(mine, bucket_idx=990 + ai, wire="fp32", algo=algo)
+        mine2 = g.clone()
+        comm.allreduce_(mine2, bucket_idx=980 + ai, wire="bf16", algo=algo)
+        torch.cuda.synchronize()
+        out[algo + "_fp32_allclose_rtol1e-3_atol1e-5"] = bool(torch.allclose(mine, theirs, rtol=1e-3, atol=1e-5))
+        out[algo + "_bf16_max_err_vs_exact"] = float((mine2.double() - exact).abs().max())
+        out[algo + "_bf16_max_abs_diff_vs_nccl"] = float((mine2 - c.float()).abs().max())
     if rank == 0:
-        print(json.dumps({"bench": "sweep_parity_vs_nccl", "fp32_allclose_rtol1e-3_atol1e-5": bool(ok),
-                          "bf16_max_err_vs_exact_libb2d": err_mine, "bf16_max_err_vs_exact_nccl": err_nccl,
-                          "bf16_libb2d_not_worse": err_mine <= err_nccl + 1e-12,
-                          "bf16_max_abs_diff_vs_nccl": float((mine2 - c.float()).abs().max())}), flush=True)
+        print(json.dumps(out), flush=True)
+    comm.close()
+    dist.destroy_process_group()
+
+
+def tune():
+    """Chunk size x exchange-CTA grid for the staged algorithms (isolated, back to back)."""
+    dist, comm, rank, world = _comm()
+    sizes = [4 << 20, 16 << 20, 64 << 20, 256 << 20]
+    iters = 20
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        b.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / iters], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    bufs = {w: torch.randn(w // 2, device="cuda") * 0.01 for w in sizes}
+    for chunk_mb in (4, 8, 16, 32, 64):
+        for ctas in (8, 16, 32, 64):
+            torch.cuda.synchronize()
+            dist.barrier()
+            comm.ctx.set_chunk_bytes(chunk_mb << 20)
+            comm.ctx.set_exch_ctas(ctas)
+            row = {"bench": "tune", "world": world, "chunk_mb": chunk_mb, "exch_ctas": ctas}
+            for si, w in enumerate(sizes):
+                for algo in ["staged"] + (["nvls"] if comm.nvls else []):
+                    ms = timed(lambda: comm.allreduce_(bufs[w], bucket_idx=100 + si, wire="bf16", algo=algo))
+                    row["%s_%dMiB_us" % (algo, w >> 20)] = round(ms * 1e3, 1)
+            if rank == 0:
+                print(json.dumps(row), flush=True)
     comm.close()
     dist.destroy_process_group()
 
@@ -190,17 +182,20 @@ def ncu_target():
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")          # control plane only; keeps NCCL kernels out of the capture
     wire_bytes = int(os.environ.get("B2D_NCU_WIRE_BYTES", str(16 << 20)))
-    algo = os.environ.get("B2D_NCU_ALGO", "two_shot")
-    comm = Communicator(rank, world, local, 1 << 30, mem="vmm", timeout_ms=5000, nvls="auto",
+    algos = os.environ.get("B2D_NCU_ALGO", "staged").split(",")
+    comm = Communicator(rank, world, local, 1 << 30, mem="vmm", timeout_ms=8000, nvls="auto",
                         max_ctas=int(os.environ.get("B2D_MAX_CTAS", "64")))
     buf = torch.randn(wire_bytes // 2, device="cuda") * 0.01
-    for i in range(6):
-        comm.allreduce_(buf, bucket_idx=0, wire="bf16", algo=algo)
-        torch.cuda.synchronize()
-        dist.barrier()
+    for ai, algo in enumerate(algos):
+        if algo.startswith("nvls") and not comm.nvls:
+            continue
+        for i in range(4):
+            comm.allreduce_(buf, bucket_idx=ai, wire="bf16", algo=algo)
+            torch.cuda.synchronize()
+            dist.barrier()
     comm.close()
     dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    {"k0": k0, "loopback": loopback, "sweep": sweep, "ncu_target": ncu_target}[sys.argv[1]]()
+    {"k0": k0, "loopback": loopback, "sweep": sweep, "tune": tune, "ncu_target": ncu_target}[sys.argv[1]]()
