@@ -457,7 +457,10 @@ def run_b200(args):
     kw = dict(num_workers=world, use_gpu=True, b200_wire=args.wire, b200_algo=args.algo, b200_mem=args.mem,
               b200_timing=True, b200_max_ctas=args.max_ctas, b200_exch_ctas=args.exch_ctas,
               b200_chunk_bytes=(args.chunk_mb << 20) if args.chunk_mb else None,
-              b200_arena_buckets=not args.no_arena_buckets)
+              b200_arena_buckets=not args.no_arena_buckets,
+              # the product sizes its arena for the model alone; the evidence blocks of this file (isolated buckets,
+              # parity cases, sweep up to 64 MiB of wire) stage extra buffers
+              b200_arena_extra_bytes=(1 << 30) if world > 1 else 0)
     if args.strategy == "sharded":
         strategy = RayShardedStrategy(**kw)
     else:
@@ -608,7 +611,12 @@ def run_b200(args):
             bound, runit = "nvlink", "GB/s"
             peak = float(link["peak_GBps"]) if link else NVLINK_FALLBACK_GBS
             peak_note = "peer link probe, %s (nominal %.0f GB/s per direction)" % (link["source"] if link else "fallback", NVLINK_NOMINAL_GBS)
-            if exch_timed > 0 and args.strategy != "sharded":
+            if args.strategy == "sharded" and exch_timed > 0:
+                # reduce-to-owner kernels (one per bucket, during backward) + the Adam-and-push kernel of the step
+                kernel_ms, timed_launches = kernel_ms + exch_ms, timed_launches + exch_timed
+                per_launch_ms = kernel_ms / max(timed_launches, 1)
+                buckets_per_step = timed_launches / args.steps
+            elif exch_timed > 0:
                 # staged exchange: the dominant kernel is the exchange kernel, timed per bucket on its own stream
                 kernel_ms, timed_launches = exch_ms, exch_timed
                 per_launch_ms = kernel_ms / max(timed_launches, 1)
@@ -643,7 +651,7 @@ def run_b200(args):
             "gpu_launches": launches_timed,
             "roofline": {"bound": bound, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": runit,
                          "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
-                         "kernel": ("k456_sharded_kernel" if args.strategy == "sharded" else
+                         "kernel": ("seg_reduce_kernel (per bucket, in backward) + adam_push_kernel (step)" if args.strategy == "sharded" else
                                     "k0_cast_scale_kernel<bf16>" if world == 1 else
                                     {3: "exch_kernel<NVLS> (staged exchange, multimem.ld_reduce + multimem.st)",
                                      5: "exch_kernel<P2P> (staged exchange, peer loads + peer stores)"}.get(last_algo, "k1/k2 fused allreduce"))

@@ -215,6 +215,52 @@ int b2d_reduce_scatter(b2d_ctx* ctx, int slot, const float* grads, float* out, s
 int b2d_allgather(b2d_ctx* ctx, float* buf, size_t n, const int64_t* shard_off,
                   void* wait_stream, void* comm_stream);
 
+/* ---- sharded path, overlapped with backward (b2d_owner.cuh) -------------------------------- */
+
+/* One run of the flat gradient space (8-element aligned) and the rank that owns it. */
+typedef struct b2d_seg {
+  int64_t flat_off, len;   /* elements; multiples of 8 */
+  int32_t owner;
+  int32_t pad_;
+} b2d_seg;
+
+#define B2D_RTO_ZERO_GRADS 0x1u  /* overwrite the local gradient segments with 0 once they are staged */
+#define B2D_RTO_ACCUMULATE 0x2u  /* reduced += sum  (gradient accumulation over several backward passes) */
+#define B2D_RTO_NVLS       0x4u  /* sum inside the NVSwitch (multimem.ld_reduce / multimem.st); needs a bound multicast object */
+
+/* Replaces: FairScale ShardedDataParallel's bucket set-up (reduce_buffer_size grouping of parameters that become
+ * ready together), reached through ray_lightning/ray_ddp_sharded.py:12.  Declare reduce bucket `bucket_id` as a set
+ * of segments of the flat gradient space.  The library sorts them by owner, merges touching runs and keeps the
+ * tables in device memory; the bucket's staging region (sum of lengths x wire width) is taken from the arena on
+ * first use.  Same call, same arguments, on every rank. */
+int b2d_bucket_register(b2d_ctx* ctx, int bucket_id, const b2d_seg* segs, int nseg, int wire);
+
+/* Replaces: FairScale's per-bucket `grad *= 1/W; dist.reduce(bucket, dst=owner)` issued from the autograd hooks
+ * while backward runs (ShardedDataParallel._get_reduce_fn, recalled; torch analogue: reduce_scatter of a
+ * ZeroRedundancyOptimizer bucket).  Every rank stages its copy of the bucket's segments (cast + scale); every owner
+ * then reads ITS segments from all ranks, adds them in rank order in fp32 and writes
+ *     reduced[flat_off - shard_off[rank] ...]  (fp32, local, the owner's shard of the flat space).
+ * `grads`: base of the flat fp32 gradient buffer.  Asynchronous on the library's internal streams after
+ * `wait_stream`; `comm_stream` waits for the result.  phases: bit 0 stage, bit 1 reduce (3 = both). */
+int b2d_reduce_to_owner(b2d_ctx* ctx, int bucket_id, float* grads, float* reduced, const int64_t* shard_off,
+                        float scale, unsigned flags, unsigned phases, void* wait_stream, void* comm_stream);
+
+/* One parameter group's Adam constants and the part of the OWN shard it covers (elements relative to shard start). */
+typedef struct b2d_adam_group {
+  int64_t lo, hi;
+  b2d_adam adam;
+  int32_t pad_;
+} b2d_adam_group;
+
+/* Replaces: OSS.step() on the owned shard + OSS._broadcast_params() (one broadcast per owner).  Applies Adam /
+ * AdamW (torch/optim/adam.py:530-547 arithmetic) to the own shard using `reduced` — per parameter group — and
+ * PUSHES the new fp32 parameters into every rank's flat parameter buffer (`params`, in the arena); when it has
+ * completed in `comm_stream` order, every rank's parameters are whole.  ngroups == 0: push only (the caller's own
+ * optimizer has updated the shard).  flags: B2D_RTO_NVLS.  phases: bit 1 step + push, bit 2 wait (6 = both). */
+int b2d_adam_push(b2d_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq, const float* reduced, size_t n,
+                  const int64_t* shard_off, const b2d_adam_group* groups, int ngroups, unsigned flags,
+                  unsigned phases, void* wait_stream, void* comm_stream);
+
 /* Replaces: nothing in the reference (dist.barrier is host side); device-side fence of this library.
  * All-ranks barrier enqueued on `stream` (also quiesces the arena before slots are re-laid out). */
 int b2d_barrier(b2d_ctx* ctx, void* stream);

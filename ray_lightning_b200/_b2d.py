@@ -33,7 +33,9 @@ EXPORTED_SYMBOLS = [
     "b2d_ctx_reset_stats", "b2d_plan", "b2d_ctx_trace", "b2d_ctx_set_tma_ctas",
     "b2d_allreduce_bucket_phased", "b2d_ctx_set_chunk_bytes", "b2d_ctx_set_exch_ctas", "b2d_ctx_set_nvls_auto",
     "b2d_peer_bw", "b2d_pool_bind", "b2d_pool_alloc", "b2d_pool_free", "b2d_ctx_set_inplace",
+    "b2d_bucket_register", "b2d_reduce_to_owner", "b2d_adam_push",
 ]
+RTO_ZERO_GRADS, RTO_ACCUMULATE, RTO_NVLS = 1, 2, 4
 
 
 class B2DUnavailableError(RuntimeError):
@@ -50,6 +52,14 @@ class AdamParams(ctypes.Structure):
     _fields_ = [("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
                 ("eps", ctypes.c_float), ("weight_decay", ctypes.c_float), ("step", ctypes.c_int32),
                 ("adamw", ctypes.c_int32), ("zero_grads", ctypes.c_int32)]
+
+
+class Seg(ctypes.Structure):
+    _fields_ = [("flat_off", ctypes.c_int64), ("len", ctypes.c_int64), ("owner", ctypes.c_int32), ("pad_", ctypes.c_int32)]
+
+
+class AdamGroup(ctypes.Structure):
+    _fields_ = [("lo", ctypes.c_int64), ("hi", ctypes.c_int64), ("adam", AdamParams), ("pad_", ctypes.c_int32)]
 
 
 class Stats(ctypes.Structure):
@@ -100,6 +110,9 @@ def _declare(lib):
         "b2d_ctx_set_inplace": [vp, c.c_int],
         "b2d_peer_bw": [vp, c.c_int, sz, c.c_int, c.c_int, c.POINTER(c.c_double)],
         "b2d_pool_bind": [vp],
+        "b2d_bucket_register": [vp, c.c_int, c.POINTER(Seg), c.c_int, c.c_int],
+        "b2d_reduce_to_owner": [vp, c.c_int, vp, vp, c.POINTER(c.c_int64), c.c_float, c.c_uint, c.c_uint, vp, vp],
+        "b2d_adam_push": [vp, vp, vp, vp, vp, sz, c.POINTER(c.c_int64), c.POINTER(AdamGroup), c.c_int, c.c_uint, c.c_uint, vp, vp],
         "b2d_sharded_step": [vp, c.c_int, vp, vp, vp, vp, sz, c.POINTER(c.c_int64), c.c_int, c.c_float,
                              c.POINTER(AdamParams), vp, vp],
         "b2d_reduce_scatter": [vp, c.c_int, vp, vp, sz, c.POINTER(c.c_int64), c.c_int, c.c_float, vp, vp],
@@ -293,6 +306,26 @@ class Context:
         off = (ctypes.c_int64 * len(shard_off))(*[int(x) for x in shard_off])
         self._check(self._lib.b2d_allgather(self._ctx, ctypes.c_void_p(buf_ptr), int(n), off,
                                             _stream_ptr(wait_stream), _stream_ptr(comm_stream)))
+
+    def bucket_register(self, bucket_id, segs, wire):
+        """segs: iterable of (flat_off, len, owner)."""
+        arr = (Seg * len(segs))(*[Seg(int(o), int(n), int(r), 0) for o, n, r in segs])
+        self._check(self._lib.b2d_bucket_register(self._ctx, int(bucket_id), arr, len(segs), int(wire)))
+
+    def reduce_to_owner(self, bucket_id, grads_ptr, reduced_ptr, shard_off, scale, flags, wait_stream, comm_stream, phases=3):
+        off = (ctypes.c_int64 * len(shard_off))(*[int(x) for x in shard_off])
+        self._check(self._lib.b2d_reduce_to_owner(self._ctx, int(bucket_id), ctypes.c_void_p(grads_ptr),
+                                                  ctypes.c_void_p(reduced_ptr), off, float(scale), int(flags), int(phases),
+                                                  _stream_ptr(wait_stream), _stream_ptr(comm_stream)))
+
+    def adam_push(self, params_ptr, m_ptr, v_ptr, reduced_ptr, n, shard_off, groups, flags, wait_stream, comm_stream, phases=6):
+        """groups: list of (lo, hi, AdamParams) relative to the own shard; empty: push only."""
+        off = (ctypes.c_int64 * len(shard_off))(*[int(x) for x in shard_off])
+        arr = (AdamGroup * max(len(groups), 1))(*[AdamGroup(int(lo), int(hi), a, 0) for lo, hi, a in groups])
+        self._check(self._lib.b2d_adam_push(self._ctx, ctypes.c_void_p(params_ptr), ctypes.c_void_p(m_ptr or 0),
+                                            ctypes.c_void_p(v_ptr or 0), ctypes.c_void_p(reduced_ptr or 0), int(n), off, arr,
+                                            len(groups), int(flags), int(phases), _stream_ptr(wait_stream),
+                                            _stream_ptr(comm_stream)))
 
     def barrier(self, stream):
         self._check(self._lib.b2d_barrier(self._ctx, _stream_ptr(stream)))

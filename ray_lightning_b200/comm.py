@@ -37,11 +37,16 @@ def _algo(a):
     return ALGO_NAMES[a] if isinstance(a, str) else int(a)
 
 
-def arena_bytes_for(total_grad_elems, extra_bytes=0):
-    """Arena size for a model with that many gradient elements: a double-buffered staging copy
-    at up to 4 B/element, twice (DDP lays its buckets out anew once after the first iteration,
-    reducer.hpp:125-151), plus slack for alignment."""
-    return int(16 * total_grad_elems + (64 << 20) + extra_bytes)
+def arena_bytes_for(total_grad_elems, extra_bytes=0, wire="fp32", arena_buckets=False):
+    """Arena size for a model with that many gradient elements.
+      bf16 wire : a double-buffered staging copy at 2 B/element; DDP lays its buckets out anew once after the first
+                  iteration (reducer.hpp:125-151) and the regions of the old layout are recycled (first fit), so
+                  6 B/element covers the transient;
+      fp32 wire : the same at 4 B/element -> 12 B/element — or, when DDP's bucket tensors themselves live in the
+                  arena (exchanged in place, no staging), the two generations of bucket storage: 10 B/element;
+    plus 64 MiB for the signal pad, alignment and small buckets."""
+    per = 6 if wire == "bf16" else (10 if arena_buckets else 12)
+    return int(per * total_grad_elems + (64 << 20) + extra_bytes)
 
 
 class _DevMem:
@@ -155,6 +160,36 @@ class _Base:
         self.ctx.reduce_scatter(slot, grads.data_ptr(), out.data_ptr(), grads.numel(), shard_off,
                                 _wire(wire), scale, ws, cs)
         return out
+
+    # ---- sharded path, overlapped with backward (b2d_owner.cuh) ------------------------------------------
+    def register_bucket(self, bucket_id, segs, wire="bf16"):
+        """Declare a reduce bucket: ``segs`` = [(flat_off, len, owner_rank)] runs of the flat gradient space."""
+        self.ctx.bucket_register(bucket_id, segs, _wire(wire))
+
+    def reduce_to_owner(self, bucket_id, grads, reduced, shard_off, scale=None, zero_grads=True, accumulate=False,
+                        nvls=False, wait_stream=None, comm_stream=None, phases=3):
+        _check_tensor(grads, self.device_index)
+        _check_tensor(reduced, self.device_index)
+        scale = (1.0 / self.world) if scale is None else scale
+        ws = torch.cuda.current_stream(grads.device) if wait_stream is None else wait_stream
+        cs = ws if comm_stream is None else comm_stream
+        flags = (_b2d.RTO_ZERO_GRADS if zero_grads else 0) | (_b2d.RTO_ACCUMULATE if accumulate else 0) | \
+                (_b2d.RTO_NVLS if nvls else 0)
+        self.ctx.reduce_to_owner(bucket_id, grads.data_ptr(), reduced.data_ptr(), shard_off, scale, flags, ws, cs, phases)
+
+    def adam_push_(self, params, exp_avg, exp_avg_sq, reduced, shard_off, groups, nvls=False, wait_stream=None,
+                   comm_stream=None, phases=6):
+        """Adam / AdamW on the own shard per parameter group, new parameters pushed into every rank's flat buffer
+        (``groups`` = [(lo, hi, dict(lr, beta1, beta2, eps, weight_decay, step, adamw))], empty: push only)."""
+        _check_tensor(params, self.device_index)
+        ws = torch.cuda.current_stream(params.device) if wait_stream is None else wait_stream
+        cs = ws if comm_stream is None else comm_stream
+        gs = [(lo, hi, AdamParams(lr=a["lr"], beta1=a["beta1"], beta2=a["beta2"], eps=a["eps"],
+                                  weight_decay=a["weight_decay"], step=int(a["step"]), adamw=int(a["adamw"]), zero_grads=0))
+              for lo, hi, a in groups]
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        self.ctx.adam_push(params.data_ptr(), ptr(exp_avg), ptr(exp_avg_sq), ptr(reduced), params.numel(), shard_off, gs,
+                           _b2d.RTO_NVLS if nvls else 0, ws, cs, phases)
 
     def allgather_(self, buf, shard_off, wait_stream=None, comm_stream=None):
         _check_tensor(buf, self.device_index)
@@ -370,6 +405,25 @@ class LoopbackGroup:
             rk.sharded_step_(grads[r], params[r], exp_avg[r], exp_avg_sq[r], shard_off,
                              wait_stream=torch.cuda.current_stream(grads[r].device), comm_stream=rk.stream, **kw)
 
+    def register_bucket(self, bucket_id, segs, wire="bf16"):
+        for rk in self.ranks:
+            rk.register_bucket(bucket_id, segs, wire)
+
+    def reduce_to_owner(self, bucket_id, grads, reduced, shard_off, **kw):
+        """Phase-major over the loopback ranks: stage everywhere, then reduce everywhere."""
+        for ph in (1, 2):
+            for r, rk in enumerate(self.ranks):
+                rk.reduce_to_owner(bucket_id, grads[r], reduced[r], shard_off, phases=ph,
+                                   wait_stream=torch.cuda.current_stream(grads[r].device), comm_stream=rk.stream, **kw)
+
+    def adam_push_(self, params, exp_avg, exp_avg_sq, reduced, shard_off, groups, **kw):
+        """groups[r]: rank r's parameter-group list.  Phase-major: step + push everywhere, then wait everywhere."""
+        for ph in (2, 4):
+            for r, rk in enumerate(self.ranks):
+                rk.adam_push_(params[r], None if exp_avg is None else exp_avg[r], None if exp_avg_sq is None else exp_avg_sq[r],
+                              None if reduced is None else reduced[r], shard_off, groups[r], phases=ph,
+                              wait_stream=torch.cuda.current_stream(params[r].device), comm_stream=rk.stream, **kw)
+
     def reduce_scatter(self, grads, outs, shard_off, **kw):
         for r, rk in enumerate(self.ranks):
             rk.reduce_scatter(grads[r], outs[r], shard_off,
@@ -424,7 +478,8 @@ class B200HookState:
 
     def __init__(self, wire="fp32", algo="auto", process_group=None, total_grad_elems=None,
                  arena_bytes=None, mem="ipc", timing=False, max_ctas=None, one_shot_max_bytes=None,
-                 nvls="auto", stream_priority=-1, timeout_ms=None, chunk_bytes=None, exch_ctas=None):
+                 nvls="auto", stream_priority=-1, timeout_ms=None, chunk_bytes=None, exch_ctas=None,
+                 arena_buckets=False, arena_extra_bytes=0):
         self.wire, self.algo = wire, algo
         self.process_group = process_group
         self.total_grad_elems = total_grad_elems
@@ -433,6 +488,7 @@ class B200HookState:
         self.one_shot_max_bytes = one_shot_max_bytes
         self.stream_priority = stream_priority
         self.timeout_ms, self.chunk_bytes, self.exch_ctas = timeout_ms, chunk_bytes, exch_ctas
+        self.arena_buckets, self.arena_extra_bytes = bool(arena_buckets), int(arena_extra_bytes)
         self.comm = None
         self.stream = None
         self.calls = 0
@@ -449,7 +505,8 @@ class B200HookState:
         if nbytes is None:
             if self.total_grad_elems is None:
                 raise ValueError("B200HookState needs total_grad_elems or arena_bytes")
-            nbytes = arena_bytes_for(self.total_grad_elems)
+            nbytes = arena_bytes_for(self.total_grad_elems, extra_bytes=self.arena_extra_bytes, wire=self.wire,
+                                     arena_buckets=self.arena_buckets)
         timeout_ms = self.timeout_ms
         if timeout_ms is None:
             # the watchdog follows the process group's own timeout (minutes), like torch's NCCL collectives

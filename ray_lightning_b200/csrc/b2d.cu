@@ -11,6 +11,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -19,6 +20,7 @@
 #include "b2d_kernels.cuh"
 #include "b2d_tma.cuh"
 #include "b2d_staged.cuh"
+#include "b2d_owner.cuh"
 
 using namespace b2d;
 
@@ -202,13 +204,24 @@ struct b2d_ctx {
   cudaEvent_t last_unstage_ev = nullptr;
   uint32_t epoch = 0;
   size_t chunk_bytes = 32u << 20;        // wire bytes per pipeline chunk
-  int exch_ctas = 32;                    // CTAs of the exchange kernel (the only one that waits for peers)
+  int exch_ctas = 64;                    // CTAs (256 threads) of the exchange kernel (the only one that waits for peers)
   int nvls_auto = 1;                     // AUTO may pick the in-switch reduction when a multicast object is bound
   int inplace = 1;                       // fp32 buckets that live in the arena are exchanged where they are
   uint64_t pool_allocs = 0, pool_digest = 1469598103934665603ull;   // FNV-1a over (offset, size) of pool allocations
   uint64_t exch_launches = 0, exch_timed = 0;
   double exch_ms = 0.0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> exch_pending;
+
+  // sharded path: reduce buckets registered by the host (segment tables live in device memory)
+  struct OwnerBucket {
+    int nseg = 0, wire = 0;
+    long long* d_flat_off = nullptr;
+    unsigned* d_start = nullptr;
+    unsigned owner_pack[B2D_MAX_WORLD + 1] = {};
+    uint32_t op_epoch = 0;
+  };
+  std::map<int, OwnerBucket> owner_buckets;
+  uint32_t push_epoch = 0;
 
   unsigned long long* trace_dev = nullptr;   // debug: per-block phase stamps of the LAST allreduce launch
   int trace_grid = 0;
@@ -220,6 +233,7 @@ struct b2d_ctx {
   int tma_ctas = 48;        // CTAs of the TMA-staged kernel (b2d_ctx_set_max_ctas caps it too)
   int tma_ctas_user = 0;
   size_t one_shot_max_bytes = 512 * 1024;
+  bool one_shot_max_user = false;
   // peer watchdog: minutes, like a process-group timeout — a rank that is late because of a slow data loader,
   // rank-0 logging or a debugger pause must not poison the CUDA context (b2d_ctx_set_timeout; 0 = never trap)
   unsigned timeout_ms = 600000;
@@ -381,8 +395,11 @@ int pick_algo(b2d_ctx* ctx, size_t n, int wire, int algo) {
   if (algo == B2D_ALGO_TWO_SHOT_TMA && (wire != B2D_WIRE_BF16 || n % 8 != 0)) return B2D_ALGO_TWO_SHOT;
   if (algo != B2D_ALGO_AUTO) return algo;
   const size_t wire_bytes = n * (wire == B2D_WIRE_BF16 ? 2 : 4);
-  // small buckets: one kernel, one barrier, every rank reads everything
-  if (wire_bytes <= ctx->one_shot_max_bytes) return B2D_ALGO_ONE_SHOT;
+  // small buckets: one kernel, one barrier, every rank reads everything.  At world 2 that moves exactly the bytes
+  // of the two-shot schemes, so it stays ahead much longer (2 x B200: 53 us at 16 MiB against 79 us staged)
+  const size_t one_shot_max = ctx->world == 2 && ctx->one_shot_max_bytes < (16u << 20) && !ctx->one_shot_max_user
+                                  ? (16u << 20) : ctx->one_shot_max_bytes;
+  if (wire_bytes <= one_shot_max) return B2D_ALGO_ONE_SHOT;
   // everything else goes through the staged exchange; the in-switch reduction pays from 4 ranks up
   // ((1 + 1/W) N w bytes per direction instead of 2 (W-1)/W N w; equal at W = 2)
   if (ctx->mc_bound && ctx->nvls_auto && ctx->world >= 4) return B2D_ALGO_NVLS;
@@ -459,9 +476,12 @@ int ensure_streams(b2d_ctx* ctx) {
   if (ctx->s_stage != nullptr) return B2D_OK;
   int lo = 0, hi = 0;   // "greatest" priority is the numerically lowest
   if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { cudaGetLastError(); lo = hi = 0; }
-  B2D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_stage, cudaStreamNonBlocking, hi));
+  // the exchange stream outranks the two streaming ones: its few CTAs take the first half-SM that frees up, so
+  // chunk c crosses NVLink while chunk c+1 is still being staged; all three outrank default-priority compute
+  const int lower = hi < lo ? hi + 1 : hi;
+  B2D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_stage, cudaStreamNonBlocking, lower));
   B2D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_xfer, cudaStreamNonBlocking, hi));
-  B2D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_unstage, cudaStreamNonBlocking, hi));
+  B2D_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->s_unstage, cudaStreamNonBlocking, lower));
   return B2D_OK;
 }
 
@@ -499,8 +519,10 @@ void slot_region_free(b2d_ctx* ctx, size_t off, size_t bytes) {
 // Arena slot of a bucket: two halves used alternately, so that a rank may start staging
 // step k+1 while a slow peer still reads step k's payload.
 int get_slot(b2d_ctx* ctx, int key, size_t half_bytes, size_t n, int wire, int algo, int grid,
-             cudaStream_t stream, size_t* stage_off, Slot** slot_out = nullptr, int* half_out = nullptr) {
+             cudaStream_t stream, size_t* stage_off, Slot** slot_out = nullptr, int* half_out = nullptr,
+             bool single = false) {
   half_bytes = round_up(half_bytes, kAlign);
+  if (single) half_bytes = round_up((half_bytes + 1) / 2, kAlign);   // one buffer: two "halves" of half the size
   Slot& s = ctx->slots[key];
   const bool same = s.half >= half_bytes && s.n == n && s.wire == wire && s.algo == algo && s.grid == grid;
   if (!same) {
@@ -533,6 +555,12 @@ int get_slot(b2d_ctx* ctx, int key, size_t half_bytes, size_t n, int wire, int a
       s.reuse_ev[0] = s.reuse_ev[1] = nullptr;
     }
     s.n = n; s.wire = wire; s.algo = algo; s.grid = grid;
+  }
+  if (single) {   // the caller guarantees a fence between consecutive uses (sharded path: the parameter exchange)
+    *stage_off = s.off;
+    if (slot_out != nullptr) *slot_out = &s;
+    if (half_out != nullptr) *half_out = 0;
+    return B2D_OK;
   }
   *stage_off = s.off + (s.parity & 1u) * s.half;
   if (slot_out != nullptr) *slot_out = &s;
@@ -598,6 +626,12 @@ void preload_staged() {
   preload_one(exch_kernel<W, false, true, true>);
 }
 template <int W>
+void preload_owner() {
+  preload_one(seg_reduce_kernel<W, true, false>); preload_one(seg_reduce_kernel<W, true, true>);
+  preload_one(seg_reduce_kernel<W, false, false>); preload_one(seg_reduce_kernel<W, false, true>);
+  preload_one(adam_push_kernel<W, false>); preload_one(adam_push_kernel<W, true>);
+}
+template <int W>
 void tma_attr() {
   if (cudaFuncSetAttribute(k2t_two_shot_tma_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes) != cudaSuccess)
     cudaGetLastError();
@@ -608,6 +642,8 @@ void preload_kernels() {
   preload_one(stage_kernel<true>); preload_one(stage_kernel<false>);
   preload_one(unstage_kernel<true>); preload_one(unstage_kernel<false>);
   preload_one(arrive_kernel); preload_one(wait_published_kernel); preload_one(peer_read_kernel);
+  preload_one(seg_stage_kernel<true>); preload_one(seg_stage_kernel<false>);
+  preload_owner<0>(); preload_owner<2>(); preload_owner<4>(); preload_owner<8>();
   preload_one(k0_cast_scale_kernel<true>);
   preload_one(k0_cast_scale_kernel<false>);
   preload_one(barrier_kernel);
@@ -1094,6 +1130,7 @@ int b2d_ctx_destroy(b2d_ctx* ctx) {
     for (auto& pr : ctx->ev_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& e : ctx->wait_ev) if (e != nullptr) cudaEventDestroy(e);
     for (auto& pr : ctx->exch_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& kv : ctx->owner_buckets) { cudaFree(kv.second.d_flat_off); cudaFree(kv.second.d_start); }
     for (auto& e : ctx->ev_ring) if (e != nullptr) cudaEventDestroy(e);
     for (cudaStream_t st : {ctx->s_stage, ctx->s_xfer, ctx->s_unstage}) if (st != nullptr) cudaStreamDestroy(st);
     if (ctx->peers.mc_arena != nullptr) vmm_unmap(ctx->peers.mc_arena, ctx->arena_bytes);
@@ -1144,6 +1181,7 @@ int b2d_ctx_set_tma_ctas(b2d_ctx* ctx, int ctas) {
 int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes) {
   if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
   ctx->one_shot_max_bytes = wire_bytes;
+  ctx->one_shot_max_user = true;
   return B2D_OK;
 }
 
@@ -1415,6 +1453,238 @@ int b2d_reduce_scatter(b2d_ctx* ctx, int slot, const float* grads, float* out, s
 int b2d_allgather(b2d_ctx* ctx, float* buf, size_t n, const int64_t* shard_off, void* wait_stream, void* comm_stream) {
   return sharded_common(ctx, 0, nullptr, buf, nullptr, nullptr, nullptr, n, shard_off, B2D_WIRE_FP32, 1.f, nullptr,
                         0, 1, 1, wait_stream, comm_stream);
+}
+
+// ---- sharded path on the staged machinery (b2d_owner.cuh) ----------------------------------------------------
+static void fill_adam_consts(const b2d_adam* adam, AdamConsts* a) {
+  a->lr = adam->lr; a->beta1 = adam->beta1; a->beta2 = adam->beta2; a->eps = adam->eps; a->weight_decay = adam->weight_decay;
+  a->one_minus_beta1 = static_cast<float>(1.0 - static_cast<double>(adam->beta1));
+  a->one_minus_beta2 = static_cast<float>(1.0 - static_cast<double>(adam->beta2));
+  // python-float (double) arithmetic of torch/optim/adam.py:503-541, cast once
+  double b1p = 1.0, b2p = 1.0;
+  for (int i = 0; i < adam->step; ++i) { b1p *= static_cast<double>(adam->beta1); b2p *= static_cast<double>(adam->beta2); }
+  a->step_size = static_cast<float>(static_cast<double>(adam->lr) / (1.0 - b1p));
+  a->inv_bc2_sqrt = 1.0f / static_cast<float>(sqrt(1.0 - b2p));
+  a->decay_mul = static_cast<float>(1.0 - static_cast<double>(adam->lr) * static_cast<double>(adam->weight_decay));
+  a->adamw = adam->adamw;
+}
+
+int b2d_bucket_register(b2d_ctx* ctx, int bucket_id, const b2d_seg* segs, int nseg, int wire) {
+  int rc = check_ready(ctx);
+  if (rc != B2D_OK) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (segs == nullptr || nseg < 1) return fail(ctx, B2D_ERR_INVALID, "a reduce bucket needs at least one segment");
+  if (wire != B2D_WIRE_FP32 && wire != B2D_WIRE_BF16) return fail(ctx, B2D_ERR_INVALID, "bad wire %d", wire);
+  const long long epp = wire == B2D_WIRE_BF16 ? 8 : 4;
+  std::vector<b2d_seg> v(segs, segs + nseg);
+  for (const b2d_seg& sgm : v) {
+    if (sgm.owner < 0 || sgm.owner >= ctx->world) return fail(ctx, B2D_ERR_INVALID, "segment owner %d out of range", sgm.owner);
+    if (sgm.flat_off < 0 || sgm.len <= 0 || sgm.flat_off % 8 != 0 || sgm.len % 8 != 0)
+      return fail(ctx, B2D_ERR_INVALID, "segments must be non-empty, 8-element aligned runs (got %lld + %lld)", (long long)sgm.flat_off, (long long)sgm.len);
+  }
+  std::stable_sort(v.begin(), v.end(), [](const b2d_seg& a, const b2d_seg& b) { return a.owner != b.owner ? a.owner < b.owner : a.flat_off < b.flat_off; });
+  std::vector<b2d_seg> m;   // merge runs that touch
+  for (const b2d_seg& sgm : v) {
+    if (!m.empty() && m.back().owner == sgm.owner && m.back().flat_off + m.back().len == sgm.flat_off) m.back().len += sgm.len;
+    else m.push_back(sgm);
+  }
+  std::vector<long long> flat(m.size());
+  std::vector<unsigned> start(m.size() + 1, 0);
+  b2d_ctx::OwnerBucket nb;
+  nb.nseg = static_cast<int>(m.size()); nb.wire = wire;
+  unsigned long long cum = 0;
+  int next_owner = 0;
+  for (size_t i = 0; i < m.size(); ++i) {
+    while (next_owner <= m[i].owner) nb.owner_pack[next_owner++] = static_cast<unsigned>(cum);
+    flat[i] = m[i].flat_off;
+    start[i] = static_cast<unsigned>(cum);
+    cum += static_cast<unsigned long long>(m[i].len / epp);
+    if (cum > 0xffffffffull) return fail(ctx, B2D_ERR_INVALID, "reduce bucket too large");
+  }
+  start[m.size()] = static_cast<unsigned>(cum);
+  while (next_owner <= ctx->world) nb.owner_pack[next_owner++] = static_cast<unsigned>(cum);
+  for (int r = ctx->world + 1; r <= B2D_MAX_WORLD; ++r) nb.owner_pack[r] = static_cast<unsigned>(cum);
+  DeviceGuard guard(ctx->device);
+  auto it = ctx->owner_buckets.find(bucket_id);
+  if (it != ctx->owner_buckets.end()) {
+    B2D_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(it->second.d_flat_off); cudaFree(it->second.d_start);
+    ctx->owner_buckets.erase(it);
+  }
+  void *a = nullptr, *b = nullptr;
+  B2D_CUDA(ctx, cudaMalloc(&a, flat.size() * sizeof(long long)));
+  B2D_CUDA(ctx, cudaMalloc(&b, start.size() * sizeof(unsigned)));
+  B2D_CUDA(ctx, cudaMemcpy(a, flat.data(), flat.size() * sizeof(long long), cudaMemcpyHostToDevice));
+  B2D_CUDA(ctx, cudaMemcpy(b, start.data(), start.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  nb.d_flat_off = static_cast<long long*>(a); nb.d_start = static_cast<unsigned*>(b);
+  ctx->owner_buckets[bucket_id] = nb;
+  return B2D_OK;
+}
+
+}  // extern "C"
+template <bool BF16, bool NVLS>
+static void launch_seg_reduce(const SegParams& P, int world, int grid, cudaStream_t st) {
+  switch (world) {
+    case 2: seg_reduce_kernel<2, BF16, NVLS><<<grid, kExThreads, 0, st>>>(P); break;
+    case 4: seg_reduce_kernel<4, BF16, NVLS><<<grid, kExThreads, 0, st>>>(P); break;
+    case 8: seg_reduce_kernel<8, BF16, NVLS><<<grid, kExThreads, 0, st>>>(P); break;
+    default: seg_reduce_kernel<0, BF16, NVLS><<<grid, kExThreads, 0, st>>>(P); break;
+  }
+}
+extern "C" {
+
+int b2d_reduce_to_owner(b2d_ctx* ctx, int bucket_id, float* grads, float* reduced, const int64_t* shard_off, float scale,
+                        unsigned flags, unsigned phases, void* wait_stream, void* comm_stream) {
+  int rc = check_ready(ctx);
+  if (rc != B2D_OK) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->owner_buckets.find(bucket_id);
+  if (it == ctx->owner_buckets.end()) return fail(ctx, B2D_ERR_STATE, "reduce bucket %d has not been registered", bucket_id);
+  if (grads == nullptr || reduced == nullptr || shard_off == nullptr) return fail(ctx, B2D_ERR_INVALID, "NULL argument");
+  if ((phases & 3u) == 0 || phases > 3u) return fail(ctx, B2D_ERR_INVALID, "bad phase mask %u (bit 0 stage, bit 1 reduce)", phases);
+  const bool nvls = (flags & B2D_RTO_NVLS) != 0;
+  if (nvls && !ctx->mc_bound) return fail(ctx, B2D_ERR_UNSUPPORTED, "NVLS requested but no multicast object is bound");
+  b2d_ctx::OwnerBucket& ob = it->second;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(ctx, B2D_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->device);
+  rc = ensure_streams(ctx);
+  if (rc != B2D_OK) return rc;
+  cudaStream_t comm = static_cast<cudaStream_t>(comm_stream);
+  const bool bf16 = ob.wire == B2D_WIRE_BF16;
+  const size_t total = ob.owner_pack[ctx->world];
+  size_t stage_off = 0;
+  Slot* slot = nullptr;
+  rc = get_slot(ctx, 0x20000000 + bucket_id, total * 16 * 2, total, ob.wire, 200, 0, comm, &stage_off, &slot, nullptr, true);
+  if (rc != B2D_OK) return rc;
+  if (phases & 1u) ob.op_epoch = ++ctx->epoch;
+  if (ob.op_epoch == 0) return fail(ctx, B2D_ERR_STATE, "reduce phase issued before the stage phase of bucket %d", bucket_id);
+
+  SegParams P{};
+  P.seg_flat_off = ob.d_flat_off; P.seg_start = ob.d_start; P.nseg = ob.nseg;
+  for (int r = 0; r <= B2D_MAX_WORLD; ++r) P.owner_pack[r] = ob.owner_pack[r];
+  P.grads = grads; P.reduced = reduced; P.shard_lo = shard_off[ctx->rank]; P.wire_off = stage_off; P.scale = scale;
+  P.zero_grads = (flags & B2D_RTO_ZERO_GRADS) ? 1 : 0; P.accumulate = (flags & B2D_RTO_ACCUMULATE) ? 1 : 0;
+  P.rank = ctx->rank; P.world = ctx->world; P.epoch = ob.op_epoch;
+  P.timeout_ns = static_cast<unsigned long long>(ctx->timeout_ms) * 1000000ull; P.diag = ctx->diag_dev; P.peers = ctx->peers;
+  cudaEvent_t es = nullptr;
+  if (phases & 1u) {
+    cudaEvent_t e = ctx->wait_ev[ctx->wait_ev_idx++ % 8];
+    B2D_CUDA(ctx, cudaEventRecord(e, static_cast<cudaStream_t>(wait_stream)));
+    B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_stage, e, 0));
+    const int grid = stream_grid(ctx, total);
+    if (bf16) seg_stage_kernel<true><<<grid, kStThreads, 0, ctx->s_stage>>>(P); else seg_stage_kernel<false><<<grid, kStThreads, 0, ctx->s_stage>>>(P);
+    ctx->launches += 1;
+    es = next_event(ctx);
+    B2D_CUDA(ctx, cudaEventRecord(es, ctx->s_stage));
+  }
+  if (phases & 2u) {
+    if (es != nullptr) B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_xfer, es, 0));
+    const size_t mine = ob.owner_pack[ctx->rank + 1] - ob.owner_pack[ctx->rank];
+    const size_t per_thread = nvls ? 8 : (kMaxLoadsInFlight / ctx->world > 1 ? kMaxLoadsInFlight / ctx->world : 1);
+    size_t grid = (mine + kExThreads * per_thread - 1) / (kExThreads * per_thread);
+    if (grid < 1) grid = 1;
+    if (grid > static_cast<size_t>(ctx->exch_ctas)) grid = ctx->exch_ctas;
+    std::pair<cudaEvent_t, cudaEvent_t> tp{nullptr, nullptr};
+    const bool timing = (ctx->flags & B2D_FLAG_TIMING) && take_timing_pair(ctx, &tp);
+    if (timing) B2D_CUDA(ctx, cudaEventRecord(tp.first, ctx->s_xfer));
+    if (bf16) { if (nvls) launch_seg_reduce<true, true>(P, ctx->world, static_cast<int>(grid), ctx->s_xfer); else launch_seg_reduce<true, false>(P, ctx->world, static_cast<int>(grid), ctx->s_xfer); }
+    else      { if (nvls) launch_seg_reduce<false, true>(P, ctx->world, static_cast<int>(grid), ctx->s_xfer); else launch_seg_reduce<false, false>(P, ctx->world, static_cast<int>(grid), ctx->s_xfer); }
+    ctx->launches += 1; ctx->exch_launches += 1;
+    if (timing) { B2D_CUDA(ctx, cudaEventRecord(tp.second, ctx->s_xfer)); ctx->exch_pending.push_back(tp); }
+    cudaEvent_t ex = next_event(ctx);
+    B2D_CUDA(ctx, cudaEventRecord(ex, ctx->s_xfer));
+    B2D_CUDA(ctx, cudaStreamWaitEvent(comm, ex, 0));
+    ctx->last_grid = static_cast<int>(grid);
+    ob.op_epoch = 0;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  ctx->last_algo = 12; ctx->last_block = kExThreads;
+  return B2D_OK;
+}
+
+int b2d_adam_push(b2d_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq, const float* reduced, size_t n,
+                  const int64_t* shard_off, const b2d_adam_group* groups, int ngroups, unsigned flags, unsigned phases,
+                  void* wait_stream, void* comm_stream) {
+  int rc = check_ready(ctx);
+  if (rc != B2D_OK) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (params == nullptr || shard_off == nullptr) return fail(ctx, B2D_ERR_INVALID, "NULL argument");
+  if (ngroups < 0 || ngroups > kMaxAdamGroups) return fail(ctx, B2D_ERR_INVALID, "at most %d parameter groups", kMaxAdamGroups);
+  if (ngroups > 0 && (groups == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || reduced == nullptr))
+    return fail(ctx, B2D_ERR_INVALID, "groups / exp_avg / exp_avg_sq / reduced are NULL");
+  if ((phases & 6u) == 0 || (phases & ~6u) != 0) return fail(ctx, B2D_ERR_INVALID, "bad phase mask %u (bit 1 step + push, bit 2 wait)", phases);
+  if (shard_off[0] != 0 || static_cast<size_t>(shard_off[ctx->world]) != n) return fail(ctx, B2D_ERR_INVALID, "shard_off must start at 0 and end at n");
+  for (int r = 0; r < ctx->world; ++r)
+    if (shard_off[r + 1] < shard_off[r] || shard_off[r] % 8 != 0 || shard_off[r + 1] % 8 != 0)
+      return fail(ctx, B2D_ERR_INVALID, "shard offsets must be non-decreasing multiples of 8");
+  const bool nvls = (flags & B2D_RTO_NVLS) != 0;
+  if (nvls && !ctx->mc_bound) return fail(ctx, B2D_ERR_UNSUPPORTED, "NVLS requested but no multicast object is bound");
+  const unsigned char* p8 = reinterpret_cast<const unsigned char*>(params);
+  if (p8 < ctx->arena || p8 + n * 4 > ctx->arena + ctx->arena_bytes)
+    return fail(ctx, B2D_ERR_INVALID, "the flat parameter buffer must live in the symmetric arena (b2d_arena_alloc)");
+  if (n == 0) return B2D_OK;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(ctx, B2D_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->device);
+  rc = ensure_streams(ctx);
+  if (rc != B2D_OK) return rc;
+  cudaStream_t comm = static_cast<cudaStream_t>(comm_stream);
+  if (phases & 2u) ctx->push_epoch = ++ctx->epoch;
+  if (ctx->push_epoch == 0) return fail(ctx, B2D_ERR_STATE, "wait phase issued before the push phase");
+  if (phases & 2u) {
+    PushParams P{};
+    P.params = params; P.param_off = static_cast<size_t>(p8 - ctx->arena);
+    P.exp_avg = exp_avg; P.exp_avg_sq = exp_avg_sq; P.reduced = reduced;
+    P.lo = shard_off[ctx->rank]; P.hi = shard_off[ctx->rank + 1];
+    P.ngroups = ngroups;
+    for (int k = 0; k < ngroups; ++k) {
+      if (groups[k].lo < 0 || groups[k].hi < groups[k].lo || groups[k].hi > P.hi - P.lo || groups[k].lo % 4 != 0 || groups[k].hi % 4 != 0)
+        return fail(ctx, B2D_ERR_INVALID, "parameter group %d covers [%lld, %lld) of a shard of %lld elements", k, (long long)groups[k].lo, (long long)groups[k].hi, (long long)(P.hi - P.lo));
+      if (groups[k].adam.step < 1) return fail(ctx, B2D_ERR_INVALID, "adam.step must be >= 1");
+      P.group_lo[k] = groups[k].lo; P.group_hi[k] = groups[k].hi;
+      fill_adam_consts(&groups[k].adam, &P.group[k]);
+    }
+    P.rank = ctx->rank; P.world = ctx->world; P.epoch = ctx->push_epoch; P.peers = ctx->peers;
+    cudaEvent_t e = ctx->wait_ev[ctx->wait_ev_idx++ % 8];
+    B2D_CUDA(ctx, cudaEventRecord(e, static_cast<cudaStream_t>(wait_stream)));
+    B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_xfer, e, 0));
+    size_t grid = (static_cast<size_t>(P.hi - P.lo) / 4 + kExThreads * 2 - 1) / (kExThreads * 2);
+    if (grid < 1) grid = 1;
+    if (grid > 128) grid = 128;
+    std::pair<cudaEvent_t, cudaEvent_t> tp{nullptr, nullptr};
+    const bool timing = (ctx->flags & B2D_FLAG_TIMING) && take_timing_pair(ctx, &tp);
+    if (timing) B2D_CUDA(ctx, cudaEventRecord(tp.first, ctx->s_xfer));
+#define B2D_PUSH(WW) { if (nvls) adam_push_kernel<WW, true><<<grid, kExThreads, 0, ctx->s_xfer>>>(P); else adam_push_kernel<WW, false><<<grid, kExThreads, 0, ctx->s_xfer>>>(P); }
+    switch (ctx->world) {
+      case 2: B2D_PUSH(2) break;
+      case 4: B2D_PUSH(4) break;
+      case 8: B2D_PUSH(8) break;
+      default: B2D_PUSH(0) break;
+    }
+#undef B2D_PUSH
+    ctx->launches += 1;
+    if (timing) { B2D_CUDA(ctx, cudaEventRecord(tp.second, ctx->s_xfer)); ctx->ev_pending.push_back(tp); }
+    ctx->last_grid = static_cast<int>(grid);
+  }
+  if (phases & 4u) {
+    ExParams XP{};
+    XP.rank = ctx->rank; XP.world = ctx->world; XP.peers = ctx->peers; XP.epoch = ctx->push_epoch;
+    XP.timeout_ns = static_cast<unsigned long long>(ctx->timeout_ms) * 1000000ull; XP.diag = ctx->diag_dev;
+    cudaEvent_t ex = next_event(ctx);
+    B2D_CUDA(ctx, cudaEventRecord(ex, ctx->s_xfer));
+    B2D_CUDA(ctx, cudaStreamWaitEvent(ctx->s_unstage, ex, 0));
+    wait_published_kernel<<<1, 32, 0, ctx->s_unstage>>>(XP);
+    ctx->launches += 1;
+    cudaEvent_t ed = next_event(ctx);
+    B2D_CUDA(ctx, cudaEventRecord(ed, ctx->s_unstage));
+    B2D_CUDA(ctx, cudaStreamWaitEvent(comm, ed, 0));
+    ctx->last_unstage_ev = ed;
+    ctx->push_epoch = 0;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  ctx->last_algo = 13; ctx->last_block = kExThreads;
+  return B2D_OK;
 }
 
 int b2d_barrier(b2d_ctx* ctx, void* stream) {

@@ -33,8 +33,11 @@
 
 namespace b2d {
 
-constexpr int kStThreads = 256;   // S / U: plain streaming CTAs, co-reside with anything
-constexpr int kExThreads = 512;   // X
+constexpr int kStThreads = 256;   // S / U: plain streaming CTAs
+// X: 256 threads x <= 128 registers = half an SM's register file.  A 512-thread / 128-register CTA needs an EMPTY SM,
+// which never comes up while the stage kernel of the next chunk (or a backward kernel) keeps refilling SMs: measured
+// on 2 x B200 the pipeline then degenerated to stage-all | exchange-all (profiles/r02_tune_2gpu_v1.jsonl).
+constexpr int kExThreads = 256;
 
 // spin until *ptr >= target (wrap-safe); trap with diagnostics after timeout_ns
 __device__ __forceinline__ void spin_until_ge(const uint32_t* ptr, uint32_t target, unsigned long long timeout_ns,
@@ -164,7 +167,7 @@ __device__ __forceinline__ uint4 scale_f32x4(const uint4& v, float s) {
 }
 
 template <int W, bool BF16, bool NVLS, bool INPLACE>
-__global__ void __launch_bounds__(kExThreads, 1) exch_kernel(const __grid_constant__ ExParams P) {
+__global__ void __launch_bounds__(kExThreads, 2) exch_kernel(const __grid_constant__ ExParams P) {
   static_assert(!(INPLACE && BF16), "in-place exchange exists for the fp32 wire only");
   constexpr int WW = W > 0 ? W : B2D_MAX_WORLD;
   const int world = W > 0 ? W : P.world;

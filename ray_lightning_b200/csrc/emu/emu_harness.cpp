@@ -14,6 +14,7 @@
 
 #include "../b2d_kernels.cuh"
 #include "../b2d_staged.cuh"
+#include "../b2d_owner.cuh"
 
 thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
 thread_local emu::Block* emu_block = nullptr;
@@ -209,6 +210,115 @@ int emu_staged_allreduce(void* h, int nvls, int bf16, int inplace, float** bufs,
       streams.emplace_back([&, r] { for (int c = 0; c < nchunks; ++c) if (WU(r, c) != 0) bad = 1; });
     }
   }
+  for (auto& t : streams) t.join();
+  return bad.load() ? -1 : 0;
+}
+
+// K11 + K12 (b2d_owner.cuh): one reduce bucket given as an owner-sorted segment table (seg_start in packs of the wire
+// format, cumulative, nseg + 1 entries; owner_pack[world + 1]).  order as in emu_staged_allreduce (0 / 1).
+int emu_reduce_to_owner(void* h, int bf16, int nvls, float** grads, float** reduced, const long long* shard_off,
+                        const long long* seg_flat_off, const unsigned* seg_start, int nseg, const unsigned* owner_pack,
+                        size_t wire_off, float scale, int zero_grads, int accumulate, unsigned epoch, int order, int use_generic_w) {
+  Group* g = static_cast<Group*>(h);
+  const int world = g->world;
+  if (wire_off + static_cast<size_t>(seg_start[nseg]) * 16 > g->arena_bytes) return -4;
+  emu::Multicast& mc = emu::multicast();
+  mc.fake_base = g->fake_mc; mc.world = world;
+  for (int r = 0; r < world; ++r) mc.arena[r] = g->arena[r];
+  const Peers peers = make_peers(*g);
+  auto mk = [&](int r) {
+    SegParams P{};
+    P.seg_flat_off = seg_flat_off; P.seg_start = seg_start; P.nseg = nseg;
+    for (int i = 0; i <= B2D_MAX_WORLD; ++i) P.owner_pack[i] = owner_pack[i <= world ? i : world];
+    P.grads = grads[r]; P.reduced = reduced[r]; P.shard_lo = shard_off[r]; P.wire_off = wire_off; P.scale = scale;
+    P.zero_grads = zero_grads; P.accumulate = accumulate; P.rank = r; P.world = world; P.epoch = epoch;
+    P.timeout_ns = 120ull * 1000000000ull; P.diag = nullptr; P.peers = peers;
+    return P;
+  };
+  auto S = [&](int r) {
+    const SegParams P = mk(r);
+    return bf16 ? launch_one(2, kStThreads, [P] { seg_stage_kernel<true>(P); }) : launch_one(2, kStThreads, [P] { seg_stage_kernel<false>(P); });
+  };
+  auto X = [&](int r) {
+    const SegParams P = mk(r);
+    auto run = [=] {
+      auto go = [&](auto w) {
+        constexpr int W = decltype(w)::value;
+        if (bf16) { if (nvls) seg_reduce_kernel<W, true, true>(P); else seg_reduce_kernel<W, true, false>(P); }
+        else { if (nvls) seg_reduce_kernel<W, false, true>(P); else seg_reduce_kernel<W, false, false>(P); }
+      };
+      if (use_generic_w) go(std::integral_constant<int, 0>{});
+      else if (world == 2) go(std::integral_constant<int, 2>{});
+      else if (world == 4) go(std::integral_constant<int, 4>{});
+      else if (world == 8) go(std::integral_constant<int, 8>{});
+      else go(std::integral_constant<int, 0>{});
+    };
+    return launch_one(2, kExThreads, run);
+  };
+  if (order == 1) {
+    for (int r = 0; r < world; ++r) if (S(r) != 0) return -1;
+    for (int r = 0; r < world; ++r) if (X(r) != 0) return -1;
+    return 0;
+  }
+  std::atomic<int> bad{0};
+  std::vector<std::thread> streams;
+  for (int r = 0; r < world; ++r) streams.emplace_back([&, r] { if (S(r) != 0 || X(r) != 0) bad = 1; });
+  for (auto& t : streams) t.join();
+  return bad.load() ? -1 : 0;
+}
+
+// K13: params live in every arena at param_off; m, v, reduced are the ranks' own-shard buffers.  One Adam group per
+// rank covering [glo[r], ghi[r]) of its shard (ngroups = 0: push only).
+int emu_adam_push(void* h, int nvls, size_t param_off, float** m, float** v, float** reduced, size_t n, const long long* shard_off,
+                  int ngroups, const long long* glo, const long long* ghi, float lr, float beta1, float beta2, float eps, float wd,
+                  int step, int adamw, unsigned epoch, int order, int use_generic_w) {
+  Group* g = static_cast<Group*>(h);
+  const int world = g->world;
+  if (param_off + n * 4 > g->arena_bytes) return -4;
+  emu::Multicast& mc = emu::multicast();
+  mc.fake_base = g->fake_mc; mc.world = world;
+  for (int r = 0; r < world; ++r) mc.arena[r] = g->arena[r];
+  const Peers peers = make_peers(*g);
+  auto X = [&](int r) {
+    PushParams P{};
+    P.params = reinterpret_cast<float*>(g->arena[r] + param_off); P.param_off = param_off;
+    P.exp_avg = m ? m[r] : nullptr; P.exp_avg_sq = v ? v[r] : nullptr; P.reduced = reduced ? reduced[r] : nullptr;
+    P.lo = shard_off[r]; P.hi = shard_off[r + 1]; P.ngroups = ngroups;
+    if (ngroups > 0) {
+      P.group_lo[0] = glo[r]; P.group_hi[0] = ghi[r];
+      AdamConsts& a = P.group[0];
+      a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = wd;
+      a.one_minus_beta1 = static_cast<float>(1.0 - static_cast<double>(beta1));
+      a.one_minus_beta2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+      double b1p = 1.0, b2p = 1.0;
+      for (int i = 0; i < step; ++i) { b1p *= static_cast<double>(beta1); b2p *= static_cast<double>(beta2); }
+      a.step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - b1p));
+      a.inv_bc2_sqrt = 1.0f / static_cast<float>(std::sqrt(1.0 - b2p));
+      a.decay_mul = static_cast<float>(1.0 - static_cast<double>(lr) * static_cast<double>(wd));
+      a.adamw = adamw;
+    }
+    P.rank = r; P.world = world; P.epoch = epoch; P.peers = peers;
+    auto run = [=] {
+      if (use_generic_w) { if (nvls) adam_push_kernel<0, true>(P); else adam_push_kernel<0, false>(P); }
+      else if (world == 2) { if (nvls) adam_push_kernel<2, true>(P); else adam_push_kernel<2, false>(P); }
+      else if (world == 4) { if (nvls) adam_push_kernel<4, true>(P); else adam_push_kernel<4, false>(P); }
+      else { if (nvls) adam_push_kernel<0, true>(P); else adam_push_kernel<0, false>(P); }
+    };
+    return launch_one(2, kExThreads, run);
+  };
+  auto Wt = [&](int r) {
+    ExParams P{};
+    P.rank = r; P.world = world; P.peers = peers; P.timeout_ns = 120ull * 1000000000ull; P.epoch = epoch;
+    return launch_one(1, 32, [P] { wait_published_kernel(P); });
+  };
+  if (order == 1) {
+    for (int r = 0; r < world; ++r) if (X(r) != 0) return -1;
+    for (int r = 0; r < world; ++r) if (Wt(r) != 0) return -1;
+    return 0;
+  }
+  std::atomic<int> bad{0};
+  std::vector<std::thread> streams;
+  for (int r = 0; r < world; ++r) streams.emplace_back([&, r] { if (X(r) != 0 || Wt(r) != 0) bad = 1; });
   for (auto& t : streams) t.join();
   return bad.load() ? -1 : 0;
 }

@@ -29,16 +29,20 @@ def partition_parameters(numels: Sequence[int], world: int, rule: str = "fairsca
     return owner
 
 
-def flat_layout(numels: Sequence[int], owner: Sequence[int], world: int, align: int = ALIGN) -> Tuple[List[int], List[int], int]:
-    """Parameters grouped by owner rank (declaration order within a rank), each start aligned.
-    Returns (param_offset[i], shard_off[0..world], total_elements)."""
+def flat_layout(numels: Sequence[int], owner: Sequence[int], world: int, align: int = ALIGN,
+                group_of: Sequence[int] = None) -> Tuple[List[int], List[int], int]:
+    """Parameters grouped by owner rank; inside a rank by optimizer parameter group (``group_of[i]``, default one
+    group), then declaration order; each start aligned.  An owner's shard and, inside it, every parameter group's
+    share are therefore contiguous.  Returns (param_offset[i], shard_off[0..world], total_elements)."""
     offsets = [0] * len(numels)
     shard_off = [0]
     cur = 0
+    groups = sorted(set(group_of)) if group_of is not None else [0]
     for r in range(world):
-        for i, n in enumerate(numels):
-            if owner[i] == r:
-                offsets[i] = cur
-                cur += -(-n // align) * align
+        for g in groups:
+            for i, n in enumerate(numels):
+                if owner[i] == r and (group_of is None or group_of[i] == g):
+                    offsets[i] = cur
+                    cur += -(-n // align) * align
         shard_off.append(cur)
     return offsets, shard_off, cur

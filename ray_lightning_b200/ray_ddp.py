@@ -36,7 +36,7 @@ from .launchers.ray_launcher import RayLauncher
 
 _B200_DEFAULTS = dict(enable=True, wire="fp32", algo="auto", mem="vmm", max_ctas=None, one_shot_max_bytes=None,
                       timing=False, nvls="auto", arena_bytes=None, timeout_ms=None, chunk_bytes=None, exch_ctas=None,
-                      arena_buckets=True)
+                      arena_buckets=True, reduce_bucket_mb=None, arena_extra_bytes=0)
 
 
 def _is_torch_bf16_hook(hook) -> bool:
@@ -112,7 +112,8 @@ class RayStrategy(DDPSpawnStrategy):
             ddp_kwargs["ddp_comm_state"] = B200HookState(
                 wire=o["wire"], algo=o["algo"], mem=o["mem"], timing=o["timing"], max_ctas=o["max_ctas"],
                 one_shot_max_bytes=o["one_shot_max_bytes"], nvls=o["nvls"], arena_bytes=o["arena_bytes"],
-                timeout_ms=o["timeout_ms"], chunk_bytes=o["chunk_bytes"], exch_ctas=o["exch_ctas"])
+                timeout_ms=o["timeout_ms"], chunk_bytes=o["chunk_bytes"], exch_ctas=o["exch_ctas"],
+                arena_buckets=o["arena_buckets"] and o["wire"] == "fp32", arena_extra_bytes=o["arena_extra_bytes"])
             ddp_kwargs["ddp_comm_hook"] = b200_allreduce_hook
 
         super().__init__(accelerator="_gpu" if use_gpu else "cpu", parallel_devices=[], cluster_environment=None,

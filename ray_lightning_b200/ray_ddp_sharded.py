@@ -23,8 +23,10 @@ class RayShardedStrategy(RayStrategy, DDPSpawnShardedStrategy):
 
     def __init__(self, *args, **kwargs):
         kwargs.setdefault("b200_enable", True)
+        kwargs.setdefault("b200_wire", "bf16")    # FairScale's reduce_fp16 analogue; fp32 with b200_wire="fp32"
         super().__init__(*args, **kwargs)
         self._shards = None
+        self._sharded_ready = False
 
     def configure_ddp(self):
         if self.root_device.type != "cuda":
@@ -35,24 +37,37 @@ class RayShardedStrategy(RayStrategy, DDPSpawnShardedStrategy):
         from .comm import Communicator, arena_bytes_for
         o = self._b200
         total = sum(p.numel() for p in self.lightning_module.parameters() if p.requires_grad)
-        nbytes = o["arena_bytes"] or arena_bytes_for(total, extra_bytes=12 * total)
+        # flat fp32 parameters (4 B/element) + one single-buffered staging copy at wire width + a gather buffer for
+        # consolidated checkpoints (4 B/element)
+        wire_w = 2 if (o["wire"] or "bf16") == "bf16" else 4
+        nbytes = o["arena_bytes"] or int((8 + wire_w) * total + (128 << 20) + o["arena_extra_bytes"])
         self._comm = Communicator(self.global_rank, self.world_size, self.root_device.index, nbytes, mem=o["mem"],
-                                  timing=o["timing"], max_ctas=o["max_ctas"], nvls=False)
-        from .sharded import FlatShards
-        self._shards = FlatShards(self.lightning_module, self._comm)
+                                  timing=o["timing"], max_ctas=o["max_ctas"], nvls=o["nvls"], timeout_ms=o["timeout_ms"],
+                                  exch_ctas=o["exch_ctas"])
+        # the flat layout follows the optimizer's parameter groups: built in setup_optimizers, once they are known
         self.model = self.lightning_module
-        self._sharded_wire = o["wire"]
+        self._sharded_wire = "bf16" if o["wire"] is None else o["wire"]
+        self._sharded_ready = True
 
     def _configure_cpu_reference(self):
         super().configure_ddp()
 
     def setup_optimizers(self, trainer):
         super().setup_optimizers(trainer)
-        if self._shards is not None:
-            from .sharded import ShardedOptimizer
+        if getattr(self, "_sharded_ready", False):
+            from .sharded import FlatShards, ShardedOptimizer, group_index_of
+            if len(self.optimizers) != 1:
+                raise ValueError("RayShardedStrategy(use_gpu=True) shards ONE optimizer over all trainable parameters; "
+                                 "got %d" % len(self.optimizers))
+            params = [p for p in self.lightning_module.parameters() if p.requires_grad]
+            self._shards = FlatShards(self.lightning_module, self._comm, wire=self._sharded_wire,
+                                      group_of=group_index_of(params, self.optimizers[0]),
+                                      reduce_bucket_mb=self._b200.get("reduce_bucket_mb") or 25.0)
+            side = torch.cuda.Stream(device=self.root_device, priority=-1)
             wrapped = []
             for opt in self.optimizers:
-                sopt = ShardedOptimizer(opt, self._shards, wire=self._sharded_wire)
+                sopt = ShardedOptimizer(opt, self._shards, wire=self._sharded_wire, stream=side,
+                                        nvls=bool(self._comm.nvls) and self.world_size >= 4)
                 for sch in self.lr_schedulers:
                     if getattr(sch, "optimizer", None) is opt:
                         sch.optimizer = sopt
@@ -93,6 +108,7 @@ class RayShardedStrategy(RayStrategy, DDPSpawnShardedStrategy):
         if comm is not None:
             torch.cuda.synchronize()
             self._shards = None
+            self.optimizers = []
             comm.close()
             self._comm = None
         super().teardown_worker()

@@ -160,3 +160,111 @@ def test_sharded_step_with_skewed_ranks(world, wire):
     for r in range(1, world):
         assert torch.equal(params[r], params[0]), r
     torch.testing.assert_close(params[0].cpu(), ref_p.detach(), rtol=1e-4, atol=1e-5)
+
+
+# ---- the backward-overlapped path: reduce buckets to their owners (K11 + K12), then Adam + push (K13) ----------
+def _buckets(numels, owner, offs, nb):
+    """Cut the parameters into nb reduce buckets in reverse declaration order (what FlatShards does)."""
+    idx = list(reversed(range(len(numels))))
+    per = -(-len(idx) // nb)
+    return [[(offs[i], -(-numels[i] // 8) * 8, owner[i]) for i in idx[k * per:(k + 1) * per]] for k in range(nb) if idx[k * per:(k + 1) * per]]
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("wire", ["fp32", "bf16"])
+def test_reduce_to_owner_bit_exact_and_zeroes_the_gradients(world, wire):
+    g = group(world)
+    numels, owner, offs, shard_off, total = layout(world, 11)
+    buckets = _buckets(numels, owner, offs, 4)
+    for b, segs in enumerate(buckets):
+        g.register_bucket(100 * (wire == "bf16") + b, segs, wire)
+    scale = float(np.float32(1.0) / np.float32(world))
+    for rep in range(2):     # twice: the second pass accumulates on the owner
+        per_rank = [torch.randn(total, generator=torch.Generator().manual_seed(40 + r + 10 * rep)) * 0.1 for r in range(world)]
+        grads = [t.cuda() for t in per_rank]
+        if rep == 0:
+            reduced = [torch.full((max(shard_off[r + 1] - shard_off[r], 8),), 7.0, device="cuda") for r in range(world)]
+            first = None
+        torch.cuda.synchronize()
+        for b in range(len(buckets)):
+            g.reduce_to_owner(100 * (wire == "bf16") + b, grads, reduced, shard_off, zero_grads=True, accumulate=rep == 1)
+        g.synchronize()
+        if wire == "fp32":
+            want = ddp_oracle.allreduce_fp32_wire(per_rank, scale)
+        else:
+            want = None
+            for t in per_rank:
+                c = ddp_oracle.wire_bf16(t, scale)
+                want = c if want is None else want + c
+        # elements that belong to no parameter (alignment gaps) carry whatever the flat buffer held: compare real elements
+        mask = torch.zeros(total, dtype=torch.bool)
+        for o, n in zip(offs, numels):
+            mask[o:o + n] = True
+        if rep == 1:
+            want = first + want
+        else:
+            first = want.clone()
+        for r in range(world):
+            lo, hi = shard_off[r], shard_off[r + 1]
+            got = reduced[r][:hi - lo].cpu()
+            assert torch.equal(got[mask[lo:hi]], want[lo:hi][mask[lo:hi]]), (world, wire, rep, r)
+            assert float(grads[r][mask.cuda()].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("adamw", [False, True])
+def test_adam_push_matches_torch_and_leaves_every_rank_whole(world, adamw):
+    """K13 with TWO parameter groups per shard (different lr / weight decay) over three steps: every rank ends with
+    the same, whole parameter vector == torch.optim.Adam(W) with the same groups on the reduced gradients."""
+    g = group(world)
+    _, _, _, shard_off, total = layout(world, 12)
+    p0 = torch.randn(total, generator=torch.Generator().manual_seed(5))
+    params = []
+    for rk in g.ranks:
+        p = rk.arena_tensor(total)
+        p.copy_(p0.cuda())
+        params.append(p)
+    n_own = [shard_off[r + 1] - shard_off[r] for r in range(world)]
+    ms = [torch.zeros(max(n, 8), device="cuda") for n in n_own]
+    vs = [torch.zeros(max(n, 8), device="cuda") for n in n_own]
+    split = [(n // 16) * 8 for n in n_own]                     # group 0: [0, split), group 1: [split, n)
+    hyp = [dict(lr=1e-2, weight_decay=0.0), dict(lr=3e-3, weight_decay=0.1)]
+    refs, opts = [], []
+    for r in range(world):
+        a = torch.nn.Parameter(p0[shard_off[r]:shard_off[r] + split[r]].clone())
+        b = torch.nn.Parameter(p0[shard_off[r] + split[r]:shard_off[r + 1]].clone())
+        refs.append((a, b))
+        cls = torch.optim.AdamW if adamw else torch.optim.Adam
+        opts.append(cls([{"params": [a], **hyp[0]}, {"params": [b], **hyp[1]}]))
+    for step in range(1, 4):
+        red = [torch.randn(max(n, 8), generator=torch.Generator().manual_seed(100 * step + r)) * 0.1 for r, n in enumerate(n_own)]
+        reduced = [t.cuda() for t in red]
+        groups = []
+        for r in range(world):
+            gs = []
+            for gi, (lo, hi) in enumerate(((0, split[r]), (split[r], n_own[r]))):
+                if hi > lo:
+                    gs.append((lo, hi, dict(lr=hyp[gi]["lr"], beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=hyp[gi]["weight_decay"],
+                                            step=step, adamw=int(adamw))))
+            groups.append(gs)
+        torch.cuda.synchronize()
+        g.adam_push_(params, ms, vs, reduced, shard_off, groups)
+        g.synchronize()
+        for r in range(world):
+            a, b = refs[r]
+            a.grad = red[r][:split[r]].clone()
+            b.grad = red[r][split[r]:n_own[r]].clone()
+            opts[r].step()
+        want = torch.cat([torch.cat([a.detach(), b.detach()]) for a, b in refs])
+        for r in range(world):
+            np.testing.assert_allclose(params[r].cpu().numpy(), want.numpy(), rtol=2e-5, atol=2e-6)
+            assert torch.equal(params[r], params[0])
+    # push only (a generic optimizer updated the shard): every rank receives every owner's values bit for bit
+    for r in range(world):
+        params[r][shard_off[r]:shard_off[r + 1]] = float(r + 1)
+    torch.cuda.synchronize()
+    g.adam_push_(params, None, None, None, shard_off, [[] for _ in range(world)])
+    g.synchronize()
+    for r in range(world):
+        for o in range(world):
+            assert bool((params[r][shard_off[o]:shard_off[o + 1]] == float(o + 1)).all())

@@ -35,6 +35,14 @@ def emu(tmp_path_factory):
     lib.emu_staged_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(FP),
                                          ctypes.c_size_t, ctypes.c_float, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_int]
+    UP = ctypes.POINTER(ctypes.c_uint)
+    LP = ctypes.POINTER(ctypes.c_longlong)
+    lib.emu_reduce_to_owner.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(FP), ctypes.POINTER(FP), LP, LP, UP,
+                                        ctypes.c_int, UP, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_uint,
+                                        ctypes.c_int, ctypes.c_int]
+    lib.emu_adam_push.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(FP), ctypes.POINTER(FP), ctypes.POINTER(FP),
+                                  ctypes.c_size_t, LP, ctypes.c_int, LP, LP, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                  ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_int]
     lib.emu_k0.argtypes = [FP, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_int]
     lib.emu_sharded_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(FP), ctypes.c_size_t, ctypes.POINTER(FP),
                                      ctypes.POINTER(FP), ctypes.c_size_t, ctypes.POINTER(ctypes.c_longlong), ctypes.c_float,
@@ -267,5 +275,111 @@ def test_reduce_scatter_and_allgather_alone_on_cpu_threads(emu, world):
         assert emu.emu_allgather(g, sig, total, off, 2) == 0
         for r in range(world):
             assert same_bits(views[r], full), r
+    finally:
+        emu.emu_group_destroy(g)
+
+
+def _seg_table(segs, world, epp):
+    """What b2d_bucket_register builds: segments sorted by (owner, offset), touching runs merged, cumulative pack starts."""
+    segs = sorted(segs, key=lambda s: (s[2], s[0]))
+    merged = []
+    for off, n, owner in segs:
+        if merged and merged[-1][2] == owner and merged[-1][0] + merged[-1][1] == off:
+            merged[-1][1] += n
+        else:
+            merged.append([off, n, owner])
+    flat, start, owner_pack, cum, nxt = [], [], [], 0, 0
+    for off, n, owner in merged:
+        while nxt <= owner:
+            owner_pack.append(cum)
+            nxt += 1
+        flat.append(off)
+        start.append(cum)
+        cum += n // epp
+    start.append(cum)
+    while nxt <= world:
+        owner_pack.append(cum)
+        nxt += 1
+    return flat, start, owner_pack
+
+
+@pytest.mark.parametrize("world,generic", [(2, 0), (4, 0), (3, 1)])
+@pytest.mark.parametrize("bf16", [0, 1])
+@pytest.mark.parametrize("nvls", [0, 1])
+def test_reduce_to_owner_and_adam_push_on_cpu_threads(emu, world, generic, bf16, nvls):
+    """K11 + K12 + K13: two reduce buckets of scattered parameter segments go to their owners (second pass accumulates),
+    then Adam on every owner's shard and the push of the new parameters; serialised phase-major order included."""
+    rng = np.random.default_rng(7)
+    numels = [int(x) for x in rng.integers(1, 900, size=11)] + [2500]
+    owner = ddp_oracle.partition_fairscale(numels, world)
+    offs, shard_off, total = ddp_oracle.shard_layout(numels, owner, world)
+    epp = 8 if bf16 else 4
+    idx = list(reversed(range(len(numels))))
+    buckets = [[(offs[i], -(-numels[i] // 8) * 8, owner[i]) for i in part] for part in (idx[:6], idx[6:])]
+    sig = emu.emu_signal_bytes()
+    g = emu.emu_group_create(world, 4 << 20)
+    off = (ctypes.c_longlong * (world + 1))(*shard_off)
+    mask = np.zeros(total, bool)
+    for o, n in zip(offs, numels):
+        mask[o:o + n] = True
+    try:
+        scale = float(np.float32(1.0) / np.float32(world))
+        n_own = [shard_off[r + 1] - shard_off[r] for r in range(world)]
+        reduced = [np.full(max(n, 8), 5.0, np.float32) for n in n_own]
+        epoch = 1
+        total_want = None
+        for rep in range(2):
+            per_rank = [torch.randn(total, generator=torch.Generator().manual_seed(31 * rep + r)) * 0.1 for r in range(world)]
+            grads = [t.numpy().copy() for t in per_rank]
+            wire_off = sig + (1 << 20)
+            for b, segs in enumerate(buckets):
+                flat, start, opack = _seg_table(segs, world, epp)
+                rc = emu.emu_reduce_to_owner(g, bf16, nvls, ptrs(grads), ptrs(reduced), off, (ctypes.c_longlong * len(flat))(*flat),
+                                             (ctypes.c_uint * len(start))(*start), len(flat), (ctypes.c_uint * len(opack))(*opack),
+                                             wire_off, scale, 1, rep, epoch, (rep + b) % 2, generic)
+                assert rc == 0
+                epoch += 1
+                wire_off += start[-1] * 16
+            if bf16 and nvls:
+                want = ddp_oracle.allreduce_bf16_wire(per_rank)      # the switch hands back a bf16 sum: one rounding more
+            elif bf16:
+                want = None
+                for t in per_rank:
+                    c = ddp_oracle.wire_bf16(t, scale)
+                    want = c if want is None else want + c
+            else:
+                want = ddp_oracle.allreduce_fp32_wire(per_rank, scale)
+            total_want = want.numpy() if rep == 0 else total_want + want.numpy()
+            for r in range(world):
+                lo, hi = shard_off[r], shard_off[r + 1]
+                m = mask[lo:hi]
+                assert same_bits(reduced[r][:hi - lo][m], total_want[lo:hi][m]), (world, bf16, nvls, rep, r)
+                assert float(np.abs(grads[r][mask]).max()) == 0.0
+        # Adam on the owners' shards + push
+        p0 = torch.randn(total, generator=torch.Generator().manual_seed(9)).numpy()
+        poff = sig + (2 << 20)
+        views = []
+        for r in range(world):
+            v = np.ctypeslib.as_array(emu.emu_arena_ptr(g, r, poff), shape=(total,))
+            v[:] = p0
+            views.append(v)
+        ms = [np.zeros(max(n, 8), np.float32) for n in n_own]
+        vs = [np.zeros(max(n, 8), np.float32) for n in n_own]
+        glo = (ctypes.c_longlong * world)(*[0] * world)
+        ghi = (ctypes.c_longlong * world)(*n_own)
+        ref = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+        opt = torch.optim.Adam([ref], lr=1e-2)
+        for step in (1, 2):
+            assert emu.emu_adam_push(g, nvls, poff, ptrs(ms), ptrs(vs), ptrs(reduced), total, off, 1, glo, ghi, 1e-2, 0.9, 0.999, 1e-8, 0.0,
+                                     step, 0, epoch, step % 2, generic) == 0
+            epoch += 1
+            full = np.zeros(total, np.float32)
+            for r in range(world):
+                full[shard_off[r]:shard_off[r + 1]] = reduced[r][:n_own[r]]
+            ref.grad = torch.from_numpy(full.copy())
+            opt.step()
+            for r in range(world):
+                assert same_bits(views[r], views[0]), (step, r)
+            np.testing.assert_allclose(views[0], ref.detach().numpy(), rtol=2e-5, atol=2e-6)
     finally:
         emu.emu_group_destroy(g)
