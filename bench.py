@@ -209,7 +209,7 @@ def parity_block(comm, dist, torch, world, rank, dev, bucket_sizes):
     failed, cases = [], 0
     key = 20000
     worst = {"fp32_vs_nccl_max_abs": 0.0, "bf16_err_vs_exact_libb2d": 0.0, "bf16_err_vs_exact_nccl": 0.0,
-             "nvls_bf16_ulps_max": 0.0}
+             "bf16_err_vs_exact_nvls": 0.0, "nvls_bf16_ulps_max": 0.0}
 
     def bits_equal(a, b):
         return torch.equal(a.view(torch.int32), b.view(torch.int32))
@@ -261,7 +261,8 @@ def parity_block(comm, dist, torch, world, rank, dev, bucket_sizes):
                     worst["fp32_vs_nccl_max_abs"] = max(worst["fp32_vs_nccl_max_abs"], float((got - nccl_fp32.cpu()).abs().max()))
                 else:
                     e = float((got.double() - exact_bf).abs().max())
-                    worst["bf16_err_vs_exact_libb2d"] = max(worst["bf16_err_vs_exact_libb2d"], e)
+                    k = "bf16_err_vs_exact_nvls" if algo.startswith("nvls") else "bf16_err_vs_exact_libb2d"
+                    worst[k] = max(worst[k], e)
                 if not ok:
                     failed.append(tag)
     # one fused sharded step (reduce-scatter -> Adam -> all-gather) against the oracle's Adam on the averaged gradients
@@ -295,7 +296,9 @@ def parity_block(comm, dist, torch, world, rank, dev, bucket_sizes):
             "contract": "P2P algorithms bit-exact vs oracle.ddp_oracle (both wires); NVLS: all ranks same bits, fp32 rtol 1e-5, "
                         "bf16 within one bf16 step of the exact sum; fp32 wire vs ncclAllReduce rtol 1e-3 / atol 1e-5",
             **{k: float("%.3g" % v) for k, v in worst.items()},
-            "bf16_libb2d_not_worse_than_nccl": worst["bf16_err_vs_exact_libb2d"] <= worst["bf16_err_vs_exact_nccl"] + 1e-12}
+            "bf16_libb2d_not_worse_than_nccl": worst["bf16_err_vs_exact_libb2d"] <= worst["bf16_err_vs_exact_nccl"] + 1e-12,
+            "note": "bf16_err_vs_exact_libb2d covers the rank-ordered P2P algorithms (one rounding of an fp32 sum); the in-switch "
+                    "reduction is reported separately (bf16_err_vs_exact_nvls, nvls_bf16_ulps_max)"}
 
 
 def allreduce_sweep(comm, dist, torch, world, rank, sizes, iters=20, symm=True):

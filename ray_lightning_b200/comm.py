@@ -26,7 +26,7 @@ from . import _b2d
 from ._b2d import ALGO_NAMES, FLAG_MEM_VMM, FLAG_TIMING, WIRE_NAMES, AdamParams, B2DError
 
 __all__ = ["Communicator", "LoopbackGroup", "B200HookState", "b200_allreduce_hook", "arena_bytes_for",
-           "arena_tensor"]
+           "arena_tensor", "ArenaBufferSync", "b200_buffer_hook"]
 
 
 def _wire(w):
@@ -448,6 +448,56 @@ class LoopbackGroup:
         for rk in self.ranks:
             rk.ctx.destroy()
         self.ranks = []
+
+
+# ---- f-3: DDP's per-forward buffer broadcast through the arena -------------------------------------------------
+class ArenaBufferSync:
+    """State of ``b200_buffer_hook``: the module's buffers (BatchNorm running statistics, counters ...) live in ONE flat
+    region of the symmetric arena; "broadcast from rank 0" is then rank 0 pushing that region into every peer's arena
+    (b2d_adam_push with no Adam groups and rank 0 owning everything) — one kernel + a one-warp wait per forward, no
+    flatten / unflatten copies and no NCCL call.  Replaces DDP._sync_buffers' coalesced ncclBroadcast
+    (torch/nn/parallel/distributed.py `_sync_buffers` / `_default_broadcast_coalesced`)."""
+
+    def __init__(self, hook_state, src=0):
+        self.hook_state, self.src = hook_state, src
+        self.flat = None
+        self.calls = 0
+
+    def adopt(self, buffers):
+        """Move every buffer into the arena (same values, same tensor objects).  Collective in the sense that every
+        rank must do it with the same buffers; called once, lazily, from the hook."""
+        comm = self.hook_state.comm
+        items = [(n, b) for n, b in buffers.items() if b is not None and b.numel() > 0]
+        offs, cur = [], 0
+        for _, b in items:
+            offs.append(cur)
+            cur += -(-b.numel() * b.element_size() // 32) * 32      # 8 fp32 elements: the push kernel's granule
+        self.nbytes = max(cur, 32)
+        raw = comm.arena_tensor(self.nbytes // 4, torch.float32)
+        self.flat = raw
+        as_bytes = raw.view(torch.uint8)
+        for (_, b), off in zip(items, offs):
+            v = as_bytes[off:off + b.numel() * b.element_size()].view(b.dtype).view(b.shape)
+            v.copy_(b.data)
+            b.data = v
+        n = self.nbytes // 4
+        self.shard_off = [0] + [n if r >= self.src else 0 for r in range(comm.world)]
+
+    def sync(self, buffers):
+        st = self.hook_state
+        if self.flat is None:
+            self.adopt(buffers)
+        cur = torch.cuda.current_stream(self.flat.device)
+        st.comm.adam_push_(self.flat, None, None, None, self.shard_off, [], nvls=False, wait_stream=cur, comm_stream=cur)
+        self.calls += 1
+
+
+def b200_buffer_hook(state: ArenaBufferSync, buffers):
+    """DDP buffer comm hook (``DistributedDataParallel._register_buffer_comm_hook``): rank 0's buffers reach every rank
+    through libb2d's peer stores instead of a coalesced ncclBroadcast."""
+    state.hook_state.ensure(next(iter(buffers.values())).device)
+    state.sync(buffers)
+    return None
 
 
 def _pg_timeout_ms(group=None):

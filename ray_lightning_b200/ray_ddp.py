@@ -19,6 +19,8 @@ copy.  New knobs ride in as keyword arguments prefixed ``b200_`` and never reach
     b200_max_ctas, b200_one_shot_max_bytes, b200_chunk_bytes, b200_exch_ctas, b200_timing, b200_nvls,
     b200_arena_buckets=True   (with gradient_as_bucket_view=True and the fp32 wire) let DDP's flat bucket tensors live
                               in the symmetric arena so that buckets are exchanged in place — no stage-in copy
+    b200_buffer_sync=True     module buffers (BatchNorm statistics) live in the arena; DDP's per-forward broadcast from
+                              rank 0 becomes one peer-store kernel instead of a coalesced ncclBroadcast
     b200_enable=True
 
 There is no CPU implementation of that hook: with ``use_gpu=False`` the strategy is the
@@ -36,7 +38,7 @@ from .launchers.ray_launcher import RayLauncher
 
 _B200_DEFAULTS = dict(enable=True, wire="fp32", algo="auto", mem="vmm", max_ctas=None, one_shot_max_bytes=None,
                       timing=False, nvls="auto", arena_bytes=None, timeout_ms=None, chunk_bytes=None, exch_ctas=None,
-                      arena_buckets=True, reduce_bucket_mb=None, arena_extra_bytes=0)
+                      arena_buckets=True, reduce_bucket_mb=None, arena_extra_bytes=0, buffer_sync=True)
 
 
 def _is_torch_bf16_hook(hook) -> bool:
@@ -197,6 +199,16 @@ class RayStrategy(DDPSpawnStrategy):
             raise RuntimeError("RayStrategy(use_gpu=True) needs a CUDA device in the worker: the B200 gradient-sync "
                                "path has no CPU fallback")
         super()._register_ddp_hooks()
+        # f-3: the per-forward buffer broadcast (BatchNorm statistics ...) goes through the arena too
+        ddp = self.model
+        if (state is not None and hasattr(state, "ensure") and self._b200["buffer_sync"] and self.world_size > 1
+                and self.root_device.type == "cuda" and hasattr(ddp, "_register_buffer_comm_hook")
+                and getattr(ddp, "broadcast_buffers", True) and any(True for _ in ddp.module.buffers())):
+            from torch.nn.parallel.distributed import _BufferCommHookLocation
+            from .comm import ArenaBufferSync, b200_buffer_hook
+            self._b200_buffer_state = ArenaBufferSync(state)
+            ddp._register_buffer_comm_hook(self._b200_buffer_state, b200_buffer_hook,
+                                           comm_hook_location=_BufferCommHookLocation.PRE_FORWARD)   # where DDP's own sync sits
 
     @property
     def b200_state(self):
@@ -207,6 +219,12 @@ class RayStrategy(DDPSpawnStrategy):
     def teardown_worker(self) -> None:
         """Worker: release the communicator before the process group goes away."""
         st = self.b200_state
+        bst = getattr(self, "_b200_buffer_state", None)
+        if bst is not None and bst.flat is not None and self.lightning_module is not None:
+            for b in self.lightning_module.buffers():        # give the buffers ordinary storage back
+                if st.comm is not None and st.comm.owns(b):
+                    b.data = b.data.clone()
+            self._b200_buffer_state = None
         self.model = None          # the Reducer's arena-backed buckets go before the arena does
         if st is not None:
             import gc

@@ -107,6 +107,10 @@ class RayShardedStrategy(RayStrategy, DDPSpawnShardedStrategy):
         comm = getattr(self, "_comm", None)
         if comm is not None:
             torch.cuda.synchronize()
+            if self._shards is not None:
+                for p in self._shards.params:        # parameters were views of the arena: give them ordinary storage back
+                    p.data = p.data.clone()
+                    p.grad = None
             self._shards = None
             self.optimizers = []
             comm.close()

@@ -138,3 +138,74 @@ def test_ddp_with_the_hook_matches_stock_ddp_and_the_oracle():
     for r in range(2):
         assert ret[r]["ok"], dict(ret[r])
         assert ret[r]["fp32"]["calls"] >= 4 and ret[r]["fp32"]["buckets_seen"] >= 2   # several buckets after the re-layout
+
+
+def _bn_worker(rank, world, port, ret):
+    """DDP's per-forward buffer broadcast (BatchNorm statistics from rank 0) through libb2d's peer
+    stores (b200_buffer_hook) instead of a coalesced ncclBroadcast — same values as stock DDP on every rank, and the
+    gradient buckets living in the arena (fp32 wire, exchanged in place) at the same time."""
+    import torch.distributed as dist
+    import torch.nn as nn
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from torch.nn.parallel.distributed import _BufferCommHookLocation
+    from ray_lightning_b200.comm import ArenaBufferSync, B200HookState, b200_allreduce_hook, b200_buffer_hook
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="env://")
+    dev = torch.device("cuda", rank % torch.cuda.device_count())
+    torch.cuda.set_device(dev)
+
+    def make():
+        torch.manual_seed(0)
+        return nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU(), nn.Conv2d(8, 4, 3), nn.BatchNorm2d(4),
+                             nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(4, 5)).to(dev)
+
+    st = None
+    try:
+        n_el = sum(p.numel() for p in make().parameters())
+        st = B200HookState(wire="fp32", total_grad_elems=n_el, mem="ipc", arena_buckets=True, arena_extra_bytes=8 << 20)
+        st.ensure(dev)
+        with st.allocate_in_arena():
+            ours = DDP(make(), device_ids=[dev.index], gradient_as_bucket_view=True)
+        symmetric = st.verify_symmetric_buckets()
+        stock = DDP(make(), device_ids=[dev.index], gradient_as_bucket_view=True)
+        ours.register_comm_hook(st, b200_allreduce_hook)
+        bst = ArenaBufferSync(st)
+        ours._register_buffer_comm_hook(bst, b200_buffer_hook, comm_hook_location=_BufferCommHookLocation.PRE_FORWARD)
+        opts = [torch.optim.SGD(m.parameters(), lr=0.1) for m in (ours, stock)]
+        ok = True
+        for it in range(5):
+            g = torch.Generator().manual_seed(100 * it + rank)
+            x, y = torch.randn(6, 3, 12, 12, generator=g).to(dev), torch.randint(0, 5, (6,), generator=g).to(dev)
+            if it == 1:                           # DDP lays its buckets out anew in the second forward: do it in the arena
+                with st.allocate_in_arena():
+                    ours.reducer._rebuild_buckets()
+                symmetric = symmetric and st.verify_symmetric_buckets()
+            for m, o in zip((ours, stock), opts):
+                o.zero_grad(set_to_none=False)
+                nn.functional.cross_entropy(m(x), y).backward()
+                o.step()
+            torch.cuda.synchronize()
+        for (n1, b1), (_, b2) in zip(ours.module.named_buffers(), stock.module.named_buffers()):
+            ok = ok and torch.equal(b1, b2) and st.comm.owns(b1)
+        for p1, p2 in zip(ours.parameters(), stock.parameters()):
+            ok = ok and torch.allclose(p1, p2, rtol=1e-5, atol=1e-7)      # world 2, fp32: one add per element
+        ret[rank] = {"ok": bool(ok), "buffer_syncs": bst.calls, "symmetric": bool(symmetric),
+                     "in_arena": dict(st.in_arena), "algo": st.comm.stats()["last_algo"]}
+        del ours
+    finally:
+        if st is not None:
+            import gc
+            gc.collect()
+            st.close()
+        dist.destroy_process_group()
+
+
+def test_buffer_broadcast_and_arena_buckets_match_stock_ddp():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bn_worker, args=(2, _port(), ret), nprocs=2, join=True)
+    for r in range(2):
+        assert ret[r]["ok"], dict(ret[r])
+        assert ret[r]["buffer_syncs"] == 5
+        assert ret[r]["symmetric"] and all(ret[r]["in_arena"].values()), dict(ret[r])

@@ -155,8 +155,10 @@ def tune():
         return float(t)
 
     bufs = {w: torch.randn(w // 2, device="cuda") * 0.01 for w in sizes}
-    for chunk_mb in (4, 8, 16, 32, 64):
-        for ctas in (8, 16, 32, 64):
+    chunks = [int(x) for x in os.environ.get("B2D_TUNE_CHUNKS", "4,8,16,32,64").split(",")]
+    ctass = [int(x) for x in os.environ.get("B2D_TUNE_CTAS", "8,16,32,64").split(",")]
+    for chunk_mb in chunks:
+        for ctas in ctass:
             torch.cuda.synchronize()
             dist.barrier()
             comm.ctx.set_chunk_bytes(chunk_mb << 20)
