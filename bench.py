@@ -339,16 +339,21 @@ def allreduce_sweep(comm, dist, torch, world, rank, sizes, iters=20, symm=True):
         n = wire_bytes // 2
         buf = torch.randn(n, device="cuda") * 0.01
         row = {"wire_bytes": wire_bytes, "elements": n}
-        algos = ["auto", "one_shot", "two_shot", "staged"] + (["nvls", "nvls_fused"] if comm.nvls else [])
+        algos = ["auto", "auto_latency", "one_shot", "two_shot", "staged"] + (["nvls", "nvls_fused"] if comm.nvls else [])
         for algo in algos:
             if algo == "one_shot" and wire_bytes > (16 << 20):
                 continue
             k = key + sizes.index(wire_bytes)
             try:
-                row["b2d_" + algo + "_ms"] = round(timed(lambda: comm.allreduce_(buf, bucket_idx=k, wire="bf16", algo=algo)), 4)
+                comm.ctx.set_auto_profile(1 if algo == "auto_latency" else 0)
+                a = "auto" if algo == "auto_latency" else algo
+                row["b2d_" + algo + "_ms"] = round(timed(lambda: comm.allreduce_(buf, bucket_idx=k, wire="bf16", algo=a)), 4)
+                if algo.startswith("auto"):
+                    row[algo + "_algo"] = comm.ctx.plan(n, 1)[0]
             except Exception as e:
                 row["b2d_" + algo + "_error"] = repr(e)[:120]
-        row["auto_algo"] = comm.ctx.plan(n, 1)[0]
+            finally:
+                comm.ctx.set_auto_profile(0)
 
         def hook_seq():
             c = buf.to(torch.bfloat16).div_(world)

@@ -144,9 +144,12 @@ const char* b2d_last_error(b2d_ctx* ctx);
 int b2d_ctx_set_timeout(b2d_ctx* ctx, unsigned timeout_ms);  /* peer-flag watchdog; default 600000 (10 min), 0 = never */
 int b2d_ctx_set_max_ctas(b2d_ctx* ctx, int max_ctas);        /* CTAs per comm kernel; default 64 */
 int b2d_ctx_set_tma_ctas(b2d_ctx* ctx, int ctas);            /* CTAs of the TMA-staged kernel; default 48 */
-int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes); /* AUTO: one-shot at or below */
-int b2d_ctx_set_chunk_bytes(b2d_ctx* ctx, size_t wire_bytes);  /* staged exchange: wire bytes per pipeline chunk; default 32 MiB */
-int b2d_ctx_set_exch_ctas(b2d_ctx* ctx, int ctas);             /* CTAs of the exchange kernel; default 32 */
+int b2d_ctx_set_one_shot_max_bytes(b2d_ctx* ctx, size_t wire_bytes); /* AUTO: one-shot at or below (default: 16 / 4 / 1 MiB at world 2 / 4 / 8) */
+int b2d_ctx_set_chunk_bytes(b2d_ctx* ctx, size_t wire_bytes);  /* staged exchange: wire bytes per pipeline chunk; default 64 MiB */
+int b2d_ctx_set_exch_ctas(b2d_ctx* ctx, int ctas);             /* CTAs (256 threads) of the exchange kernel; default 64 (NVLS: half) */
+#define B2D_PROFILE_OVERLAP 0   /* AUTO assumes the exchange overlaps compute (the DDP hook): staged pipeline above the one-shot range */
+#define B2D_PROFILE_LATENCY 1   /* AUTO assumes an isolated call: single-kernel algorithms up to ~100 MiB */
+int b2d_ctx_set_auto_profile(b2d_ctx* ctx, int profile);       /* default B2D_PROFILE_OVERLAP */
 int b2d_ctx_set_inplace(b2d_ctx* ctx, int enable);             /* exchange arena-resident fp32 buckets in place? default 1 */
 int b2d_ctx_set_nvls_auto(b2d_ctx* ctx, int enable);           /* may AUTO pick B2D_ALGO_NVLS when multicast is bound? default 1 */
 
@@ -260,6 +263,24 @@ typedef struct b2d_adam_group {
 int b2d_adam_push(b2d_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq, const float* reduced, size_t n,
                   const int64_t* shard_off, const b2d_adam_group* groups, int ngroups, unsigned flags,
                   unsigned phases, void* wait_stream, void* comm_stream);
+
+/* ---- optimizer step inside backward, per DDP bucket (f-2) ----------------------------------- */
+
+/* Replaces: torch's `_hook_then_optimizer` (torch/distributed/algorithms/ddp_comm_hooks/optimizer_overlap_hooks.py:
+ * 131-163), the optional overlapped-optimizer companion of the comm hook reached through
+ * ray_lightning/ray_ddp.py:112-116 (ddp_comm_hook / ddp_comm_wrapper).  Declare which parameters (device pointers,
+ * fp32) tile DDP bucket `bucket_id` (GradBucket.parameters() / gradients(): first bucket element and element count
+ * of each, in bucket order), and where each parameter's optimizer state lives (one tensor per parameter, the caller's:
+ * state1 = momentum buffer | exp_avg, state2 = exp_avg_sq; NULL arrays when the optimizer keeps none). */
+int b2d_optim_register(b2d_ctx* ctx, int bucket_id, float* const* params, float* const* state1, float* const* state2,
+                       const int64_t* bucket_off, const int64_t* numel, int nparam);
+
+/* Apply one optimizer step to the bucket's parameters from its (already averaged) gradients `grads` on `stream`:
+ * kind 0 = torch.optim.SGD (hp->lr, hp->weight_decay, `momentum`; dampening 0, no nesterov; momentum buffers
+ * zero-initialised), kind 1 = torch.optim.Adam / AdamW (all of *hp).  Issue it behind b2d_allreduce_bucket on the
+ * same comm stream. */
+int b2d_bucket_optim(b2d_ctx* ctx, int bucket_id, const float* grads, size_t n, int kind, const b2d_adam* hp,
+                     float momentum, void* stream);
 
 /* Replaces: nothing in the reference (dist.barrier is host side); device-side fence of this library.
  * All-ranks barrier enqueued on `stream` (also quiesces the arena before slots are re-laid out). */

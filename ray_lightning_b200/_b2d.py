@@ -33,8 +33,10 @@ EXPORTED_SYMBOLS = [
     "b2d_ctx_reset_stats", "b2d_plan", "b2d_ctx_trace", "b2d_ctx_set_tma_ctas",
     "b2d_allreduce_bucket_phased", "b2d_ctx_set_chunk_bytes", "b2d_ctx_set_exch_ctas", "b2d_ctx_set_nvls_auto",
     "b2d_peer_bw", "b2d_pool_bind", "b2d_pool_alloc", "b2d_pool_free", "b2d_ctx_set_inplace",
-    "b2d_bucket_register", "b2d_reduce_to_owner", "b2d_adam_push",
+    "b2d_bucket_register", "b2d_reduce_to_owner", "b2d_adam_push", "b2d_ctx_set_auto_profile",
+    "b2d_optim_register", "b2d_bucket_optim",
 ]
+PROFILE_OVERLAP, PROFILE_LATENCY = 0, 1
 RTO_ZERO_GRADS, RTO_ACCUMULATE, RTO_NVLS = 1, 2, 4
 
 
@@ -108,6 +110,9 @@ def _declare(lib):
         "b2d_ctx_set_exch_ctas": [vp, c.c_int],
         "b2d_ctx_set_nvls_auto": [vp, c.c_int],
         "b2d_ctx_set_inplace": [vp, c.c_int],
+        "b2d_ctx_set_auto_profile": [vp, c.c_int],
+        "b2d_optim_register": [vp, c.c_int, c.POINTER(vp), c.POINTER(vp), c.POINTER(vp), c.POINTER(c.c_int64), c.POINTER(c.c_int64), c.c_int],
+        "b2d_bucket_optim": [vp, c.c_int, vp, sz, c.c_int, c.POINTER(AdamParams), c.c_float, vp],
         "b2d_peer_bw": [vp, c.c_int, sz, c.c_int, c.c_int, c.POINTER(c.c_double)],
         "b2d_pool_bind": [vp],
         "b2d_bucket_register": [vp, c.c_int, c.POINTER(Seg), c.c_int, c.c_int],
@@ -264,6 +269,9 @@ class Context:
     def set_nvls_auto(self, enable):
         self._check(self._lib.b2d_ctx_set_nvls_auto(self._ctx, int(bool(enable))))
 
+    def set_auto_profile(self, profile):
+        self._check(self._lib.b2d_ctx_set_auto_profile(self._ctx, int(profile)))
+
     def set_inplace(self, enable):
         self._check(self._lib.b2d_ctx_set_inplace(self._ctx, int(bool(enable))))
 
@@ -326,6 +334,17 @@ class Context:
                                             ctypes.c_void_p(v_ptr or 0), ctypes.c_void_p(reduced_ptr or 0), int(n), off, arr,
                                             len(groups), int(flags), int(phases), _stream_ptr(wait_stream),
                                             _stream_ptr(comm_stream)))
+
+    def optim_register(self, bucket_id, param_ptrs, state1_ptrs, state2_ptrs, bucket_offs, numels):
+        n = len(param_ptrs)
+        arr = lambda ps: (ctypes.c_void_p * n)(*[int(p) for p in ps]) if ps is not None else None
+        self._check(self._lib.b2d_optim_register(
+            self._ctx, int(bucket_id), arr(param_ptrs), arr(state1_ptrs), arr(state2_ptrs),
+            (ctypes.c_int64 * n)(*[int(o) for o in bucket_offs]), (ctypes.c_int64 * n)(*[int(x) for x in numels]), n))
+
+    def bucket_optim(self, bucket_id, grads_ptr, n, kind, hp, momentum, stream):
+        self._check(self._lib.b2d_bucket_optim(self._ctx, int(bucket_id), ctypes.c_void_p(grads_ptr), int(n), int(kind),
+                                               ctypes.byref(hp), float(momentum), _stream_ptr(stream)))
 
     def barrier(self, stream):
         self._check(self._lib.b2d_barrier(self._ctx, _stream_ptr(stream)))

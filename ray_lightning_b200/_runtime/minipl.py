@@ -794,8 +794,10 @@ def _load_optimizer_state(self, states):
     for opt, st in zip(self.optimizers, states):
         try:
             opt.load_state_dict(copy.deepcopy(st))
-        except Exception:
-            pass  # a different world size re-shards the optimizer: weights resume, moments restart
+        except Exception as e:   # never silently: a resume that drops the optimizer state trains differently
+            import warnings
+            warnings.warn("optimizer state of %s could not be restored from the checkpoint (%r): weights resume, "
+                          "optimizer state restarts" % (type(opt).__name__, e))
 
 
 Strategy.load_optimizer_state = _load_optimizer_state

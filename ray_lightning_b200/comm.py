@@ -26,7 +26,7 @@ from . import _b2d
 from ._b2d import ALGO_NAMES, FLAG_MEM_VMM, FLAG_TIMING, WIRE_NAMES, AdamParams, B2DError
 
 __all__ = ["Communicator", "LoopbackGroup", "B200HookState", "b200_allreduce_hook", "arena_bytes_for",
-           "arena_tensor", "ArenaBufferSync", "b200_buffer_hook"]
+           "arena_tensor", "ArenaBufferSync", "b200_buffer_hook", "InBackwardOptimizer"]
 
 
 def _wire(w):
@@ -450,6 +450,112 @@ class LoopbackGroup:
         self.ranks = []
 
 
+# ---- f-2: the optimizer step inside backward, bucket by bucket --------------------------------------------------
+class InBackwardOptimizer(torch.optim.Optimizer):
+    """Wraps the user's SGD / Adam / AdamW: the step of every DDP bucket's parameters runs on the comm stream right
+    behind that bucket's allreduce (b2d_bucket_optim, K14) — overlapped with the rest of backward, no separate pass
+    over the parameters afterwards — and ``step()`` only advances the step count.  What torch offers as
+    ``_hook_then_optimizer`` (optimizer_overlap_hooks.py:131-163).  Same hyper-parameters (lr schedulers act on this
+    object), state per parameter in torch's own state-dict layout.  One backward per step (no gradient accumulation);
+    one parameter group."""
+
+    def __init__(self, base, hook_state):
+        if len(base.param_groups) != 1:
+            raise ValueError("optimizer-in-backward supports one parameter group")
+        g = base.param_groups[0]
+        if isinstance(base, torch.optim.SGD):
+            if g.get("nesterov") or g.get("dampening", 0) != 0 or g.get("maximize"):
+                raise ValueError("optimizer-in-backward SGD: no nesterov / dampening / maximize")
+            self.kind = 0
+        elif type(base) in (torch.optim.Adam, torch.optim.AdamW):
+            if g.get("amsgrad") or g.get("maximize") or g.get("capturable") or isinstance(g.get("lr"), torch.Tensor):
+                raise ValueError("optimizer-in-backward Adam: no amsgrad / maximize / capturable / tensor lr")
+            self.kind = 1
+        else:
+            raise ValueError("optimizer-in-backward supports SGD, Adam and AdamW (got %s)" % type(base).__name__)
+        self._base_cls = type(base)
+        d = {k: v for k, v in g.items() if k != "params"}
+        d["params"] = list(g["params"])
+        super().__init__([d], dict(base.defaults))
+        self._steps = 0
+        self._pstate = {}       # id(param) -> (state1, state2)
+        self._tables = {}       # bucket index -> layout signature
+        self.applied = 0
+        hook_state.in_backward = self
+
+    def _states(self, p):
+        st = self._pstate.get(id(p))
+        if st is None:
+            g = self.param_groups[0]
+            s1 = torch.zeros_like(p, memory_format=torch.contiguous_format) if (self.kind == 1 or g.get("momentum", 0) != 0) else None
+            s2 = torch.zeros_like(p, memory_format=torch.contiguous_format) if self.kind == 1 else None
+            st = self._pstate[id(p)] = (s1, s2)
+        return st
+
+    def apply_bucket(self, comm, bucket, buf, stream):
+        """Called by b200_allreduce_hook right after the bucket's exchange has been enqueued."""
+        params, grads = bucket.parameters(), bucket.gradients()
+        sig = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(params, grads))
+        idx = bucket.index()
+        if self._tables.get(idx) != sig:
+            if any(p.dtype != torch.float32 or not p.is_contiguous() for p in params):
+                raise ValueError("optimizer-in-backward needs contiguous fp32 parameters")
+            offs = [(g.data_ptr() - buf.data_ptr()) // 4 for g in grads]
+            st = [self._states(p) for p in params]
+            comm.ctx.optim_register(idx, [p.data_ptr() for p in params],
+                                    None if st[0][0] is None else [s[0].data_ptr() for s in st],
+                                    None if st[0][1] is None else [s[1].data_ptr() for s in st],
+                                    offs, [p.numel() for p in params])
+            self._tables[idx] = sig
+        g = self.param_groups[0]
+        if self.kind == 0:
+            hp = AdamParams(lr=float(g["lr"]), beta1=0.0, beta2=0.0, eps=0.0, weight_decay=float(g.get("weight_decay", 0.0)),
+                            step=self._steps + 1, adamw=0, zero_grads=0)
+            mom = float(g.get("momentum", 0.0))
+        else:
+            hp = AdamParams(lr=float(g["lr"]), beta1=float(g["betas"][0]), beta2=float(g["betas"][1]), eps=float(g["eps"]),
+                            weight_decay=float(g["weight_decay"]), step=self._steps + 1,
+                            adamw=int(self._base_cls is torch.optim.AdamW), zero_grads=0)
+            mom = 0.0
+        comm.ctx.bucket_optim(idx, buf.data_ptr(), buf.numel(), self.kind, hp, mom, stream)
+        self.applied += 1
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self._steps += 1      # the updates themselves ran during backward; DDP's finalize already waited for them
+        return loss
+
+    def state_dict(self):
+        g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        params = self.param_groups[0]["params"]
+        g["params"] = list(range(len(params)))
+        state = {}
+        for i, p in enumerate(params):
+            st = self._pstate.get(id(p))
+            if st is None or self._steps == 0:
+                continue
+            if self.kind == 0:
+                if st[0] is not None:
+                    state[i] = {"momentum_buffer": st[0].detach().clone()}
+            else:
+                state[i] = {"step": torch.tensor(float(self._steps)), "exp_avg": st[0].detach().clone(),
+                            "exp_avg_sq": st[1].detach().clone()}
+        return {"state": state, "param_groups": [g]}
+
+    def load_state_dict(self, sd):
+        self.param_groups[0].update({k: v for k, v in sd["param_groups"][0].items() if k != "params"})
+        params = self.param_groups[0]["params"]
+        for i, st in sd.get("state", {}).items():
+            p = params[int(i)]
+            s1, s2 = self._states(p)
+            if self.kind == 0 and "momentum_buffer" in st and s1 is not None:
+                s1.copy_(st["momentum_buffer"])
+            elif self.kind == 1:
+                s1.copy_(st["exp_avg"]); s2.copy_(st["exp_avg_sq"])
+                self._steps = int(st["step"])
+
+
 # ---- f-3: DDP's per-forward buffer broadcast through the arena -------------------------------------------------
 class ArenaBufferSync:
     """State of ``b200_buffer_hook``: the module's buffers (BatchNorm running statistics, counters ...) live in ONE flat
@@ -544,6 +650,7 @@ class B200HookState:
         self.calls = 0
         self.seen = {}   # bucket index -> elements, as last seen (introspection for benchmarks/tests)
         self.in_arena = {}  # bucket index -> does the Reducer's bucket storage live in the symmetric arena?
+        self.in_backward = None   # an InBackwardOptimizer, when the optimizer step rides behind every bucket (f-2)
         self._pool = self._pool_alloc = None
 
     def ensure(self, device):
@@ -602,7 +709,7 @@ class B200HookState:
 
     def __getstate__(self):
         d = dict(self.__dict__)
-        d["comm"], d["stream"], d["_pool"], d["_pool_alloc"] = None, None, None, None
+        d["comm"], d["stream"], d["_pool"], d["_pool_alloc"], d["in_backward"] = None, None, None, None, None
         return d
 
     def close(self):
@@ -629,6 +736,8 @@ def b200_allreduce_hook(state: B200HookState, bucket: dist.GradBucket) -> torch.
     state.calls += 1
     state.seen[bucket.index()] = buf.numel()
     state.in_arena[bucket.index()] = comm.owns(buf)
+    if state.in_backward is not None:
+        state.in_backward.apply_bucket(comm, bucket, buf, state.stream)
     fut = torch.futures.Future(devices=[buf.device])
     with torch.cuda.stream(state.stream):
         fut.set_result(buf)

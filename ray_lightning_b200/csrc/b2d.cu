@@ -203,7 +203,7 @@ struct b2d_ctx {
   size_t ev_ring_idx = 0;
   cudaEvent_t last_unstage_ev = nullptr;
   uint32_t epoch = 0;
-  size_t chunk_bytes = 32u << 20;        // wire bytes per pipeline chunk
+  size_t chunk_bytes = 64u << 20;        // wire bytes per pipeline chunk (host launch cost grows with the chunk count)
   int exch_ctas = 64;                    // CTAs (256 threads) of the exchange kernel (the only one that waits for peers)
   int nvls_auto = 1;                     // AUTO may pick the in-switch reduction when a multicast object is bound
   int inplace = 1;                       // fp32 buckets that live in the arena are exchanged where they are
@@ -222,6 +222,8 @@ struct b2d_ctx {
   };
   std::map<int, OwnerBucket> owner_buckets;
   uint32_t push_epoch = 0;
+  struct OptimBucket { int nseg = 0; size_t n = 0; float** d_ptr = nullptr; unsigned* d_start = nullptr; };   // d_ptr: [3][nseg] params | state1 | state2
+  std::map<int, OptimBucket> optim_buckets;
 
   unsigned long long* trace_dev = nullptr;   // debug: per-block phase stamps of the LAST allreduce launch
   int trace_grid = 0;
@@ -232,8 +234,9 @@ struct b2d_ctx {
   int max_ctas = 64;
   int tma_ctas = 48;        // CTAs of the TMA-staged kernel (b2d_ctx_set_max_ctas caps it too)
   int tma_ctas_user = 0;
-  size_t one_shot_max_bytes = 512 * 1024;
+  size_t one_shot_max_bytes = 1024 * 1024;
   bool one_shot_max_user = false;
+  int auto_profile = B2D_PROFILE_OVERLAP;
   // peer watchdog: minutes, like a process-group timeout — a rank that is late because of a slow data loader,
   // rank-0 logging or a debugger pause must not poison the CUDA context (b2d_ctx_set_timeout; 0 = never trap)
   unsigned timeout_ms = 600000;
@@ -395,15 +398,27 @@ int pick_algo(b2d_ctx* ctx, size_t n, int wire, int algo) {
   if (algo == B2D_ALGO_TWO_SHOT_TMA && (wire != B2D_WIRE_BF16 || n % 8 != 0)) return B2D_ALGO_TWO_SHOT;
   if (algo != B2D_ALGO_AUTO) return algo;
   const size_t wire_bytes = n * (wire == B2D_WIRE_BF16 ? 2 : 4);
-  // small buckets: one kernel, one barrier, every rank reads everything.  At world 2 that moves exactly the bytes
-  // of the two-shot schemes, so it stays ahead much longer (2 x B200: 53 us at 16 MiB against 79 us staged)
-  const size_t one_shot_max = ctx->world == 2 && ctx->one_shot_max_bytes < (16u << 20) && !ctx->one_shot_max_user
-                                  ? (16u << 20) : ctx->one_shot_max_bytes;
-  if (wire_bytes <= one_shot_max) return B2D_ALGO_ONE_SHOT;
-  // everything else goes through the staged exchange; the in-switch reduction pays from 4 ranks up
-  // ((1 + 1/W) N w bytes per direction instead of 2 (W-1)/W N w; equal at W = 2)
-  if (ctx->mc_bound && ctx->nvls_auto && ctx->world >= 4) return B2D_ALGO_NVLS;
-  return B2D_ALGO_STAGED;
+  const int W = ctx->world;
+  const bool nvls = ctx->mc_bound && ctx->nvls_auto && W >= 4;
+  // Small buckets: one kernel, one barrier, every rank reads everything.  Measured cross-over on B200s behind an
+  // NVSwitch (profiles/r02_sweep_{2gpu_v2,4,8}.jsonl): 16 MiB at world 2 (same bytes as any two-shot scheme),
+  // 4 MiB at world 4, 1 MiB at world 8.
+  size_t one_shot_max = ctx->one_shot_max_bytes;
+  if (!ctx->one_shot_max_user) one_shot_max = W == 2 ? (16u << 20) : (W <= 4 ? (4u << 20) : (1u << 20));
+  if (ctx->auto_profile == B2D_PROFILE_LATENCY) {
+    // an isolated call, nothing to overlap with: the single-kernel algorithms are ahead of the staged pipeline's
+    // four launches up to ~100 MiB; beyond that the chunk pipeline hides the cast passes behind the link
+    if (wire_bytes <= one_shot_max) return B2D_ALGO_ONE_SHOT;
+    if (nvls && W >= 8) return wire_bytes <= (96u << 20) ? B2D_ALGO_NVLS_FUSED : B2D_ALGO_NVLS;
+    return B2D_ALGO_TWO_SHOT;
+  }
+  // B2D_PROFILE_OVERLAP (default; the DDP hook): the exchange shares the GPU with backward kernels.  The staged
+  // pipeline's streaming kernels never spin and its exchange kernel holds a few half-SMs only, which is worth more
+  // than the ~10 us it loses in isolation: ResNet-50 on 8 x B200 29.8k img/s against 28.0k with the fused two-shot
+  // (round 1) and 27.3k with NCCL's bf16 hook (profiles/r02_v1_bench_n8*.json).
+  if (wire_bytes <= (W == 2 ? one_shot_max : (one_shot_max < (1u << 20) ? one_shot_max : (1u << 20)))) return B2D_ALGO_ONE_SHOT;
+  // the in-switch reduction pays from 4 ranks up ((1 + 1/W) N w bytes per direction instead of 2 (W-1)/W N w)
+  return nvls ? B2D_ALGO_NVLS : B2D_ALGO_STAGED;
 }
 
 // macro-tile size (packs) of the TMA kernel for a given grid: spread the slice over the grid, 8..4096
@@ -428,7 +443,9 @@ int exch_grid(const b2d_ctx* ctx, size_t chunk_packs, int algo) {
   const size_t per_thread = algo == B2D_ALGO_NVLS ? 8 : (ctx->world <= 8 && kMaxLoadsInFlight / ctx->world > 1 ? kMaxLoadsInFlight / ctx->world : 1);
   size_t grid = (slice + kExThreads * per_thread - 1) / (kExThreads * per_thread);
   if (grid < 1) grid = 1;
-  if (grid > static_cast<size_t>(ctx->exch_ctas)) grid = ctx->exch_ctas;
+  // multimem keeps the link busy from fewer CTAs (8 x B200, 256 MiB: 790 us with 32 CTAs, 835 with 64)
+  const size_t cap = algo == B2D_ALGO_NVLS ? static_cast<size_t>(ctx->exch_ctas > 1 ? ctx->exch_ctas / 2 : 1) : static_cast<size_t>(ctx->exch_ctas);
+  if (grid > cap) grid = cap;
   return static_cast<int>(grid);
 }
 
@@ -644,6 +661,7 @@ void preload_kernels() {
   preload_one(arrive_kernel); preload_one(wait_published_kernel); preload_one(peer_read_kernel);
   preload_one(seg_stage_kernel<true>); preload_one(seg_stage_kernel<false>);
   preload_owner<0>(); preload_owner<2>(); preload_owner<4>(); preload_owner<8>();
+  preload_one(bucket_optim_kernel);
   preload_one(k0_cast_scale_kernel<true>);
   preload_one(k0_cast_scale_kernel<false>);
   preload_one(barrier_kernel);
@@ -1131,6 +1149,7 @@ int b2d_ctx_destroy(b2d_ctx* ctx) {
     for (auto& e : ctx->wait_ev) if (e != nullptr) cudaEventDestroy(e);
     for (auto& pr : ctx->exch_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& kv : ctx->owner_buckets) { cudaFree(kv.second.d_flat_off); cudaFree(kv.second.d_start); }
+    for (auto& kv : ctx->optim_buckets) { cudaFree(kv.second.d_ptr); cudaFree(kv.second.d_start); }
     for (auto& e : ctx->ev_ring) if (e != nullptr) cudaEventDestroy(e);
     for (cudaStream_t st : {ctx->s_stage, ctx->s_xfer, ctx->s_unstage}) if (st != nullptr) cudaStreamDestroy(st);
     if (ctx->peers.mc_arena != nullptr) vmm_unmap(ctx->peers.mc_arena, ctx->arena_bytes);
@@ -1195,6 +1214,12 @@ int b2d_ctx_set_exch_ctas(b2d_ctx* ctx, int ctas) {
   if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
   if (ctas < 1 || ctas > B2D_MAX_BLOCKS) return fail(ctx, B2D_ERR_INVALID, "exchange ctas must be in [1, %d]", B2D_MAX_BLOCKS);
   ctx->exch_ctas = ctas;
+  return B2D_OK;
+}
+int b2d_ctx_set_auto_profile(b2d_ctx* ctx, int profile) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  if (profile != B2D_PROFILE_OVERLAP && profile != B2D_PROFILE_LATENCY) return fail(ctx, B2D_ERR_INVALID, "bad profile %d", profile);
+  ctx->auto_profile = profile;
   return B2D_OK;
 }
 int b2d_ctx_set_inplace(b2d_ctx* ctx, int enable) {
@@ -1684,6 +1709,71 @@ int b2d_adam_push(b2d_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   ctx->last_algo = 13; ctx->last_block = kExThreads;
+  return B2D_OK;
+}
+
+// ---- optimizer in backward (f-2) ----------------------------------------------------------------------------------
+int b2d_optim_register(b2d_ctx* ctx, int bucket_id, float* const* params, float* const* state1, float* const* state2,
+                       const int64_t* bucket_off, const int64_t* numel, int nparam) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (params == nullptr || bucket_off == nullptr || numel == nullptr || nparam < 1) return fail(ctx, B2D_ERR_INVALID, "bad parameter table");
+  std::vector<float*> ptr(3 * static_cast<size_t>(nparam), nullptr);
+  std::vector<unsigned> start(nparam + 1);
+  long long cur = 0;
+  for (int i = 0; i < nparam; ++i) {
+    if (bucket_off[i] != cur || numel[i] <= 0 || params[i] == nullptr)
+      return fail(ctx, B2D_ERR_INVALID, "parameters must tile the bucket in order (parameter %d at %lld, expected %lld)", i, (long long)bucket_off[i], cur);
+    ptr[i] = params[i]; start[i] = static_cast<unsigned>(cur);
+    if (state1 != nullptr) ptr[nparam + i] = state1[i];
+    if (state2 != nullptr) ptr[2 * nparam + i] = state2[i];
+    cur += numel[i];
+    if (cur > 0xffffffffll) return fail(ctx, B2D_ERR_INVALID, "bucket too large");
+  }
+  start[nparam] = static_cast<unsigned>(cur);
+  DeviceGuard guard(ctx->device);
+  auto it = ctx->optim_buckets.find(bucket_id);
+  if (it != ctx->optim_buckets.end()) {
+    B2D_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(it->second.d_ptr); cudaFree(it->second.d_start);
+    ctx->optim_buckets.erase(it);
+  }
+  b2d_ctx::OptimBucket ob;
+  ob.nseg = nparam; ob.n = static_cast<size_t>(cur);
+  void *a = nullptr, *b = nullptr;
+  B2D_CUDA(ctx, cudaMalloc(&a, ptr.size() * sizeof(float*)));
+  B2D_CUDA(ctx, cudaMalloc(&b, start.size() * sizeof(unsigned)));
+  B2D_CUDA(ctx, cudaMemcpy(a, ptr.data(), ptr.size() * sizeof(float*), cudaMemcpyHostToDevice));
+  B2D_CUDA(ctx, cudaMemcpy(b, start.data(), start.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  ob.d_ptr = static_cast<float**>(a); ob.d_start = static_cast<unsigned*>(b);
+  ctx->optim_buckets[bucket_id] = ob;
+  return B2D_OK;
+}
+
+int b2d_bucket_optim(b2d_ctx* ctx, int bucket_id, const float* grads, size_t n, int kind, const b2d_adam* hp, float momentum,
+                     void* stream) {
+  if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->optim_buckets.find(bucket_id);
+  if (it == ctx->optim_buckets.end()) return fail(ctx, B2D_ERR_STATE, "bucket %d has no parameter table (b2d_optim_register)", bucket_id);
+  if (it->second.n != n) return fail(ctx, B2D_ERR_INVALID, "bucket %d has %zu elements, its parameter table covers %zu", bucket_id, n, it->second.n);
+  if (grads == nullptr || hp == nullptr || (kind != 0 && kind != 1)) return fail(ctx, B2D_ERR_INVALID, "bad argument");
+  if (kind == 1 && hp->step < 1) return fail(ctx, B2D_ERR_INVALID, "Adam needs step >= 1");
+  DeviceGuard guard(ctx->device);
+  OptimParams P{};
+  P.param_ptr = it->second.d_ptr; P.seg_start = it->second.d_start; P.nseg = it->second.nseg;
+  P.state1_ptr = it->second.d_ptr + it->second.nseg; P.state2_ptr = it->second.d_ptr + 2 * it->second.nseg;
+  P.grads = grads; P.n = n; P.kind = kind;
+  P.lr = hp->lr; P.momentum = momentum; P.weight_decay = hp->weight_decay;
+  if (kind == 1) fill_adam_consts(hp, &P.adam);
+  size_t grid = (n + kStThreads * 4 - 1) / (kStThreads * 4);
+  if (grid < 1) grid = 1;
+  const size_t cap = static_cast<size_t>(ctx->sm_count) * 2;
+  if (grid > cap) grid = cap;
+  bucket_optim_kernel<<<static_cast<int>(grid), kStThreads, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  ctx->launches += 1;
   return B2D_OK;
 }
 

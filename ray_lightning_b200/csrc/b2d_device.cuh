@@ -224,6 +224,18 @@ __device__ __forceinline__ float wire_bf16_value(float g, float scale) {
   return round_bf16(round_bf16(g) * scale);
 }
 
+// ---- system-scope fence ------------------------------------------------------------------
+// Release / acquire around the flag exchange need fence.acq_rel, not the sequentially consistent fence that
+// __threadfence_system() emits (SASS MEMBAR.SC.SYS + ERRBAR + CCTL.IVALL): every payload access that follows an
+// acquire is itself a system-scope load (ld.relaxed.sys) or runs in a later kernel.
+__device__ __forceinline__ void fence_sys() {
+#ifdef B2D_EMU
+  __threadfence_system();
+#else
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+#endif
+}
+
 // ---- inter-GPU block barrier ------------------------------------------------------------
 // Block `b` of this rank meets block `b` of every peer.  Everything the block's threads
 // wrote before the call (own arena, peers' arenas) is visible to the peer blocks after
@@ -238,7 +250,7 @@ __device__ __forceinline__ void block_barrier(const Peers& peers, int rank, int 
   uint32_t val = 0;
   if (threadIdx.x < world) {
     val = self->ctr[b] + 1u;
-    __threadfence_system();  // release: the block's earlier writes, cumulative over bar.sync
+    fence_sys();  // release: the block's earlier writes, cumulative over bar.sync
     st_flag(&peers.signal[threadIdx.x]->flag[val & 1u][b][rank], val);
     const uint32_t* mine = &self->flag[val & 1u][b][threadIdx.x];
     uint32_t got = ld_flag(mine);
@@ -254,13 +266,13 @@ __device__ __forceinline__ void block_barrier(const Peers& peers, int rank, int 
             diag->expect = val;
             diag->got = got;
             diag->code = 1;
-            __threadfence_system();
+            fence_sys();
           }
           __trap();
         }
       }
     }
-    __threadfence_system();  // acquire
+    fence_sys();  // acquire
   }
   __syncthreads();
   if (threadIdx.x == 0) self->ctr[b] = val;
@@ -277,7 +289,7 @@ __device__ __forceinline__ uint32_t barrier_arrive(const Peers& peers, int rank,
   const int b = blockIdx.x;
   const uint32_t val = peers.signal[rank]->ctr[b] + 1u;
   if (threadIdx.x < world) {
-    __threadfence_system();
+    fence_sys();
     st_flag(&peers.signal[threadIdx.x]->flag[val & 1u][b][rank], val);
   }
   return val;
@@ -300,12 +312,12 @@ __device__ __forceinline__ uint32_t poll_arrived(const Peers& peers, int rank, i
         while (first < world && ((done_mask >> first) & 1u)) ++first;
         diag->rank = rank; diag->block = b; diag->peer = first; diag->expect = val; diag->got = ld_flag(mine + first);
         diag->code = 1;
-        __threadfence_system();
+        fence_sys();
       }
       __trap();
     }
   }
-  __threadfence_system();  // acquire
+  fence_sys();  // acquire
   return mask;
 }
 

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kExThreads, 2) seg_reduce_kernel(const __grid_
   Signal* self = P.peers.signal[P.rank];
   if (threadIdx.x < static_cast<unsigned>(world)) {
     spin_until_ge(&self->staged[threadIdx.x], P.epoch, P.timeout_ns, P.diag, P.rank, threadIdx.x);
-    __threadfence_system();
+    fence_sys();
   }
   __syncthreads();
   const unsigned q0 = P.owner_pack[P.rank], q1 = P.owner_pack[P.rank + 1];
@@ -226,6 +226,52 @@ __global__ void __launch_bounds__(kExThreads, 2) adam_push_kernel(const __grid_c
     }
   }
   arrive_when_grid_done(P.peers, P.rank, P.world, 1, P.epoch);
+}
+
+// ---- K14: optimizer step of one DDP bucket, right behind its allreduce --------------------------
+// Replaces torch's `_hook_then_optimizer` (optimizer_overlap_hooks.py:131-163: allreduce future .then(functional
+// optimizer per parameter)).  The bucket's averaged gradients are contiguous; its parameters are separate
+// allocations, so the kernel walks a small table (first bucket element of each parameter, cumulative) and touches
+// parameters with coalesced 4-byte accesses.  Optimizer state (momentum buffer, or exp_avg / exp_avg_sq) is one
+// tensor per parameter, owned by the caller (it survives DDP's bucket re-layout).  Arithmetic follows torch.optim.SGD (sgd.py `_single_tensor_sgd`, dampening 0, no
+// nesterov) and torch.optim.Adam / AdamW (adam_update above), fp32.
+struct OptimParams {
+  float* const* param_ptr;      // [nseg] device table: start of each parameter
+  const unsigned* seg_start;    // [nseg + 1] first bucket element of each parameter, cumulative
+  int nseg;
+  const float* grads;           // the bucket (averaged gradients), n elements
+  size_t n;
+  float* const* state1_ptr;     // [nseg] momentum buffer | exp_avg      of each parameter
+  float* const* state2_ptr;     // [nseg] unused          | exp_avg_sq
+  int kind;                     // 0 SGD, 1 Adam / AdamW
+  float lr, momentum, weight_decay;
+  AdamConsts adam;
+};
+
+__global__ void __launch_bounds__(kStThreads) bucket_optim_kernel(const __grid_constant__ OptimParams P) {
+  const size_t gt = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < P.n; e += gt) {
+    const int s = seg_find(P.seg_start, P.nseg, static_cast<unsigned>(e));
+    const size_t k = e - P.seg_start[s];
+    float* pp = P.param_ptr[s] + k;
+    float g = P.grads[e], p = *pp;
+    if (P.kind == 0) {
+      if (P.weight_decay != 0.f) g = fmaf(P.weight_decay, p, g);      // grad = grad.add(param, alpha=weight_decay)
+      if (P.momentum != 0.f) {
+        float* bp = P.state1_ptr[s] + k;
+        const float b = __fadd_rn(__fmul_rn(P.momentum, *bp), g);      // buf.mul_(momentum).add_(grad): two roundings
+        *bp = b;
+        g = b;
+      }
+      *pp = fmaf(-P.lr, g, p);                                         // param.add_(grad, alpha=-lr)
+    } else {
+      float* mp = P.state1_ptr[s] + k;
+      float* vp = P.state2_ptr[s] + k;
+      float m = *mp, v = *vp;
+      adam_update(g, p, m, v, P.adam);
+      *pp = p; *mp = m; *vp = v;
+    }
+  }
 }
 
 }  // namespace b2d

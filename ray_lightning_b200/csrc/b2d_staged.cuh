@@ -51,7 +51,7 @@ __device__ __forceinline__ void spin_until_ge(const uint32_t* ptr, uint32_t targ
       if (diag != nullptr) {
         diag->rank = rank; diag->block = blockIdx.x; diag->peer = peer; diag->expect = target; diag->got = got;
         diag->code = 1;
-        __threadfence_system();
+        fence_sys();
       }
       __trap();
     }
@@ -71,18 +71,18 @@ __device__ __forceinline__ void arrive_when_grid_done(const Peers& peers, int ra
   __syncthreads();
   Signal* self = peers.signal[rank];
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    fence_sys();
     const unsigned ticket = atomicAdd(&self->done_ctr[which], 1u);
     const int last = ticket == gridDim.x - 1u;
     if (last) {
       self->done_ctr[which] = 0u;   // the next kernel of this kind starts after this one ended (same stream)
-      __threadfence_system();
+      fence_sys();
     }
     s_last = last;
   }
   __syncthreads();
   if (s_last && threadIdx.x < static_cast<unsigned>(world)) {
-    __threadfence_system();
+    fence_sys();
     uint32_t* slot = which == 0 ? &peers.signal[threadIdx.x]->staged[rank] : &peers.signal[threadIdx.x]->published[rank];
     st_flag(slot, epoch);
   }
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kStThreads) stage_kernel(const __grid_constant
 // in-place mode: nothing to stage, only say "my bucket is ready" (stream-ordered after its producer)
 __global__ void __launch_bounds__(32) arrive_kernel(const __grid_constant__ StParams P) {
   if (threadIdx.x < static_cast<unsigned>(P.world)) {
-    __threadfence_system();
+    fence_sys();
     st_flag(&P.peers.signal[threadIdx.x]->staged[P.rank], P.epoch);
   }
 }
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kExThreads, 2) exch_kernel(const __grid_consta
   Signal* self = P.peers.signal[P.rank];
   if (threadIdx.x < static_cast<unsigned>(world)) {
     spin_until_ge(&self->staged[threadIdx.x], P.epoch, P.timeout_ns, P.diag, P.rank, threadIdx.x);
-    __threadfence_system();   // acquire
+    fence_sys();   // acquire
   }
   __syncthreads();
 
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kExThreads, 2) exch_kernel(const __grid_consta
 __global__ void __launch_bounds__(32) wait_published_kernel(const __grid_constant__ ExParams P) {
   if (threadIdx.x < static_cast<unsigned>(P.world)) {
     spin_until_ge(&P.peers.signal[P.rank]->published[threadIdx.x], P.epoch, P.timeout_ns, P.diag, P.rank, threadIdx.x);
-    __threadfence_system();
+    fence_sys();
   }
 }
 

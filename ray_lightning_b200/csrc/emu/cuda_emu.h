@@ -97,7 +97,8 @@ inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst
 
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
-inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }   // no contraction, one rounding
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }   // no contraction, one rounding
 
 // fp32 -> bf16 bits, round to nearest even, NaN kept quiet (what cvt.rn.bf16.f32 does)
 inline uint16_t emu_f32_to_bf16(float x) {

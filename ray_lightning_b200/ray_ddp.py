@@ -21,6 +21,9 @@ copy.  New knobs ride in as keyword arguments prefixed ``b200_`` and never reach
                               in the symmetric arena so that buckets are exchanged in place — no stage-in copy
     b200_buffer_sync=True     module buffers (BatchNorm statistics) live in the arena; DDP's per-forward broadcast from
                               rank 0 becomes one peer-store kernel instead of a coalesced ncclBroadcast
+    b200_optimizer_in_backward=False   SGD / Adam / AdamW applied per DDP bucket right behind its allreduce, on the comm
+                              stream, while backward continues (torch's `_hook_then_optimizer`, fused); one backward
+                              per step, one parameter group
     b200_enable=True
 
 There is no CPU implementation of that hook: with ``use_gpu=False`` the strategy is the
@@ -38,7 +41,7 @@ from .launchers.ray_launcher import RayLauncher
 
 _B200_DEFAULTS = dict(enable=True, wire="fp32", algo="auto", mem="vmm", max_ctas=None, one_shot_max_bytes=None,
                       timing=False, nvls="auto", arena_bytes=None, timeout_ms=None, chunk_bytes=None, exch_ctas=None,
-                      arena_buckets=True, reduce_bucket_mb=None, arena_extra_bytes=0, buffer_sync=True)
+                      arena_buckets=True, reduce_bucket_mb=None, arena_extra_bytes=0, buffer_sync=True, optimizer_in_backward=False)
 
 
 def _is_torch_bf16_hook(hook) -> bool:
@@ -189,6 +192,20 @@ class RayStrategy(DDPSpawnStrategy):
                 self.b200_arena_buckets_active = st.verify_symmetric_buckets()
             self._b200_steps += 1
         return super().training_step(*args)
+
+    def setup_optimizers(self, trainer) -> None:
+        super().setup_optimizers(trainer)
+        st = self.b200_state
+        if st is not None and self._b200["optimizer_in_backward"] and self.root_device.type == "cuda":
+            from .comm import InBackwardOptimizer
+            if len(self.optimizers) != 1:
+                raise ValueError("b200_optimizer_in_backward needs exactly one optimizer")
+            base = self.optimizers[0]
+            wrapped = InBackwardOptimizer(base, st)
+            for sch in self.lr_schedulers:
+                if getattr(sch, "optimizer", None) is base:
+                    sch.optimizer = wrapped
+            self.optimizers = [wrapped]
 
     def _register_ddp_hooks(self) -> None:
         """Size the symmetric arena from the wrapped module, then let the base class register the hook."""

@@ -209,3 +209,72 @@ def test_buffer_broadcast_and_arena_buckets_match_stock_ddp():
         assert ret[r]["ok"], dict(ret[r])
         assert ret[r]["buffer_syncs"] == 5
         assert ret[r]["symmetric"] and all(ret[r]["in_arena"].values()), dict(ret[r])
+
+
+def _inbw_worker(rank, world, port, ret):
+    """the optimizer step applied per DDP bucket right behind its allreduce (K14) == stock DDP followed by
+    torch's own optimizer.step(), across DDP's bucket re-layout, for SGD(momentum, weight decay) and AdamW."""
+    import torch.distributed as dist
+    import torch.nn as nn
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from ray_lightning_b200.comm import B200HookState, InBackwardOptimizer, b200_allreduce_hook
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="env://")
+    dev = torch.device("cuda", rank % torch.cuda.device_count())
+    torch.cuda.set_device(dev)
+
+    def make():
+        torch.manual_seed(0)
+        return nn.Sequential(nn.Linear(37, 531), nn.ReLU(), nn.Linear(531, 257), nn.ReLU(), nn.Linear(257, 11)).to(dev)
+
+    ok, info, states = True, {}, []
+    try:
+        for name, mk in (("sgd", lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-2)),
+                         ("adamw", lambda ps: torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.05))):
+            kw = dict(device_ids=[dev.index], bucket_cap_mb=0.25, gradient_as_bucket_view=True)
+            ours, stock = DDP(make(), **kw), DDP(make(), **kw)
+            st = B200HookState(wire="fp32", total_grad_elems=sum(p.numel() for p in stock.parameters()), mem="ipc")
+            states.append(st)
+            ours.register_comm_hook(st, b200_allreduce_hook)
+            opt = InBackwardOptimizer(mk(ours.parameters()), st)
+            sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)
+            ref_opt = mk(stock.parameters())
+            ref_sched = torch.optim.lr_scheduler.StepLR(ref_opt, step_size=2, gamma=0.5)
+            for it in range(6):
+                g = torch.Generator().manual_seed(100 * it + rank)
+                x, y = torch.randn(8, 37, generator=g).to(dev), torch.randint(0, 11, (8,), generator=g).to(dev)
+                before = [p.detach().clone() for p in ours.parameters()]
+                opt.zero_grad(set_to_none=False)
+                nn.functional.cross_entropy(ours(x), y).backward()
+                torch.cuda.synchronize()
+                moved = all(not torch.equal(a, b) for a, b in zip(before, ours.parameters()))   # updated INSIDE backward
+                ok = ok and moved
+                opt.step(); sched.step()
+                ref_opt.zero_grad(set_to_none=False)
+                nn.functional.cross_entropy(stock(x), y).backward()
+                ref_opt.step(); ref_sched.step()
+                torch.cuda.synchronize()
+            for a, b in zip(ours.parameters(), stock.parameters()):
+                ok = ok and torch.allclose(a, b, rtol=2e-5, atol=2e-6)
+            sd, ref_sd = opt.state_dict(), ref_opt.state_dict()
+            ok = ok and sorted(sd["state"].keys()) == sorted(ref_sd["state"].keys())
+            for i, s in ref_sd["state"].items():
+                for k, v in s.items():
+                    if isinstance(v, torch.Tensor) and v.dim() > 0:
+                        ok = ok and torch.allclose(sd["state"][i][k], v, rtol=2e-5, atol=2e-6)
+            info[name] = {"applied": opt.applied, "buckets": len(st.seen)}
+        ret[rank] = {"ok": bool(ok), **info}
+    finally:
+        for st in states:
+            st.close()
+        dist.destroy_process_group()
+
+
+def test_optimizer_in_backward_matches_stock_ddp_plus_optimizer():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_inbw_worker, args=(2, _port(), ret), nprocs=2, join=True)
+    for r in range(2):
+        assert ret[r]["ok"], dict(ret[r])
+        assert ret[r]["sgd"]["applied"] >= 6 * 2 and ret[r]["adamw"]["applied"] >= 6 * 2

@@ -99,3 +99,32 @@ def test_sharded_strategy_two_workers(tmpdir, ray_gpu):
         assert torch.equal(v, p.cpu())
     st = ckpt["optimizer_states"][0]["state"]
     assert set(st.keys()) == {0, 1} and st[0]["exp_avg"].shape == (2, 32) and st[1]["exp_avg_sq"].shape == (2,)
+
+
+def test_sharded_resume_with_fewer_workers_on_gpu(tmpdir, ray_gpu):
+    """The reference's downsize contract on the GPU path (ray_lightning/tests/test_ddp_sharded.py:118-137): fit with 2
+    sharded workers, then resume the consolidated checkpoint with ONE worker (a different flat layout and owner table)."""
+    n = ray_gpu
+    share = {"GPU": 1} if n >= 2 else {"GPU": 0.5}
+    if n < 2:
+        os.environ["PL_TORCH_DISTRIBUTED_BACKEND"] = "gloo"
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = AdamBoringModel()
+        trainer = get_trainer(tmpdir, strategy=RayShardedStrategy(num_workers=2, use_gpu=True, resources_per_worker=dict(share)),
+                              max_epochs=1)
+        trainer.fit(model)
+        path = trainer.checkpoint_callback.best_model_path
+        ckpt = torch.load(path, weights_only=False)
+        assert len(ckpt["optimizer_states"][0]["state"]) == 2 and ckpt["optimizer_states"][0]["state"][0]["step"] > 0
+        model2 = AdamBoringModel()
+        trainer2 = get_trainer(os.path.join(str(tmpdir), "resume"), strategy=RayShardedStrategy(num_workers=1, use_gpu=True),
+                               max_epochs=2, resume_from_checkpoint=path)
+        trainer2.fit(model2)
+    assert trainer2.state.finished
+    resumed = AdamBoringModel.load_from_checkpoint(trainer2.checkpoint_callback.best_model_path)
+    assert resumed.val_epoch == 2
+    ck2 = torch.load(trainer2.checkpoint_callback.best_model_path, weights_only=False)
+    # Adam's step count continued from the checkpoint instead of restarting
+    assert float(ck2["optimizer_states"][0]["state"][0]["step"]) > float(ckpt["optimizer_states"][0]["state"][0]["step"])

@@ -199,5 +199,33 @@ def ncu_target():
     dist.destroy_process_group()
 
 
+def ncu_loopback():
+    """Single-GPU target for `ncu --set full`: W loopback ranks run the staged exchange of one ResNet-50-sized bucket
+    (7 564 264 elements) phase-major, so every kernel (stage | exchange | wait | write-back, bf16 and fp32 wire, in place)
+    can be profiled one at a time.  Peer accesses stay on the device here; HBM-side behaviour is what this shows."""
+    world = int(os.environ.get("B2D_NCU_WORLD", "2"))
+    n = int(os.environ.get("B2D_NCU_ELEMS", "7564264"))
+    g = LoopbackGroup(world, 0, arena_bytes=1 << 30, timeout_ms=20000)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    for wire in ("bf16", "fp32"):
+        bufs = [torch.randn(n, device="cuda") * 0.01 for _ in range(world)]
+        for it in range(3):
+            flush.add_(1.0)
+            torch.cuda.synchronize()
+            g.allreduce_(bufs, bucket_idx=1 + (wire == "fp32"), wire=wire, algo="staged")
+            g.synchronize()
+    abufs = []
+    for rk in g.ranks:
+        a = rk.arena_tensor(n)
+        a.normal_()
+        abufs.append(a)
+    for it in range(3):
+        flush.add_(1.0)
+        torch.cuda.synchronize()
+        g.allreduce_(abufs, bucket_idx=9, wire="fp32", algo="staged")
+        g.synchronize()
+    g.close()
+
+
 if __name__ == "__main__":
-    {"k0": k0, "loopback": loopback, "sweep": sweep, "tune": tune, "ncu_target": ncu_target}[sys.argv[1]]()
+    {"k0": k0, "loopback": loopback, "sweep": sweep, "tune": tune, "ncu_target": ncu_target, "ncu_loopback": ncu_loopback}[sys.argv[1]]()
