@@ -1,6 +1,7 @@
 """Sharded training example (role of ray_lightning/examples/ray_ddp_sharded_example.py:16-71): a
 transformer LM trained with RayShardedStrategy; a callback reports epoch time and peak CUDA
-memory per worker (the reference's CUDACallback :16-45, minus its two scalar allreduces).
+memory averaged over the workers (the reference's CUDACallback :16-45, including its two scalar
+allreduces :33-36 — they run on the control-plane process group, the only collectives this example issues itself).
 
     python -m ray_lightning_b200.examples.ray_ddp_sharded_example --num-workers 2 --use-gpu
 """
@@ -61,10 +62,20 @@ class CUDACallback(Callback):
         self.t0 = time.time()
 
     def on_train_epoch_end(self, trainer, pl_module):
-        if torch.cuda.is_available():
+        dev = trainer.strategy.root_device
+        peak = 0.0
+        if dev.type == "cuda":
             torch.cuda.synchronize()
-            print("rank %d: epoch %.2f s, peak %.1f MiB" % (trainer.global_rank, time.time() - self.t0,
-                                                            torch.cuda.max_memory_allocated() / 2 ** 20), flush=True)
+            peak = torch.cuda.max_memory_allocated() / 2 ** 20
+        stats = torch.tensor([peak, time.time() - self.t0], dtype=torch.float64, device=dev)
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(stats[0:1], op=torch.distributed.ReduceOp.SUM)   # peak memory  (reference :33-34)
+            torch.distributed.all_reduce(stats[1:2], op=torch.distributed.ReduceOp.SUM)   # epoch time   (reference :35-36)
+            world = torch.distributed.get_world_size()
+        if trainer.global_rank == 0:
+            print("Average Epoch time: %.2f seconds" % (float(stats[1]) / world), flush=True)
+            print("Average Peak memory %.2f MiB" % (float(stats[0]) / world), flush=True)
 
 
 if __name__ == "__main__":
