@@ -449,7 +449,10 @@ int exch_grid(const b2d_ctx* ctx, size_t chunk_packs, int algo) {
   return static_cast<int>(grid);
 }
 
-int stream_grid(const b2d_ctx* ctx, size_t packs) {   // S / U: plain streaming kernels, 8 packs per thread
+// S / U: plain streaming kernels.  At most ONE wave (4 CTAs of 256 threads per SM, __launch_bounds__(256, 4)): a grid a
+// few CTAs larger than the machine holds costs a whole second wave — ncu on a 7.5 M-element bucket showed 462 CTAs
+// against 444 slots and 23 us where K0 moves the same bytes in 11 (profiles/r02_ncu_staged_full.md).
+int stream_grid(const b2d_ctx* ctx, size_t packs) {
   size_t grid = (packs + kStThreads * 8 - 1) / (kStThreads * 8);
   if (grid < 1) grid = 1;
   const size_t cap = static_cast<size_t>(ctx->sm_count) * 4;

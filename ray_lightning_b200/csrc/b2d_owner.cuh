@@ -56,7 +56,7 @@ __device__ __forceinline__ int seg_find(const unsigned* seg_start, int nseg, uns
 
 // ---- K11 -------------------------------------------------------------------------------------------------
 template <bool BF16>
-__global__ void __launch_bounds__(kStThreads) seg_stage_kernel(const __grid_constant__ SegParams P) {
+__global__ void __launch_bounds__(kStThreads, 4) seg_stage_kernel(const __grid_constant__ SegParams P) {
   constexpr int EPP = BF16 ? 8 : 4;
   constexpr int B = BF16 ? 4 : 8;
   const unsigned total = P.seg_start[P.nseg];

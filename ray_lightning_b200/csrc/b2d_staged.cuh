@@ -100,7 +100,7 @@ struct StParams {
 
 // ---- S -------------------------------------------------------------------------------------------------
 template <bool BF16>
-__global__ void __launch_bounds__(kStThreads) stage_kernel(const __grid_constant__ StParams P) {
+__global__ void __launch_bounds__(kStThreads, 4) stage_kernel(const __grid_constant__ StParams P) {
   constexpr int EPP = BF16 ? 8 : 4;
   constexpr int B = BF16 ? 4 : 8;   // 8 x 16-byte loads in flight per thread
   const size_t npacks = (P.n + EPP - 1) / EPP;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(32) arrive_kernel(const __grid_constant__ StPa
 
 // ---- U -------------------------------------------------------------------------------------------------
 template <bool BF16>
-__global__ void __launch_bounds__(kStThreads) unstage_kernel(const __grid_constant__ StParams P) {
+__global__ void __launch_bounds__(kStThreads, 4) unstage_kernel(const __grid_constant__ StParams P) {
   constexpr int EPP = BF16 ? 8 : 4;
   constexpr int B = 8;
   const size_t npacks = (P.n + EPP - 1) / EPP;

@@ -145,10 +145,17 @@ def test_auto_picks_one_shot_then_the_staged_exchange(world):
     # no multicast object on one GPU: the P2P variant; at world 2 one-shot moves the same bytes and keeps winning up to 16 MiB
     assert ctx.plan(8 << 20, _b2d.WIRE_BF16)[0] == (_b2d.ALGO_ONE_SHOT if world == 2 else _b2d.ALGO_STAGED)
     assert ctx.plan(32 << 20, _b2d.WIRE_BF16)[0] == _b2d.ALGO_STAGED
-    per_rank = rank_inputs(world, 300001)
+    per_rank = rank_inputs(world, 1200001)       # 2.3 MiB of bf16 wire: above the one-shot range from world 4 up
     bufs = run(world, per_rank, "bf16", "auto", 7001)
     assert same_bits(bufs[0], oracle(per_rank, "bf16"))
     assert ctx.stats()["last_algo"] == (_b2d.ALGO_STAGED if world != 2 else _b2d.ALGO_ONE_SHOT)
+    for rk in g.ranks:
+        rk.ctx.set_auto_profile(_b2d.PROFILE_LATENCY)      # an isolated call: the single-kernel two-shot
+    try:
+        assert ctx.plan(32 << 20, _b2d.WIRE_BF16)[0] == _b2d.ALGO_TWO_SHOT
+    finally:
+        for rk in g.ranks:
+            rk.ctx.set_auto_profile(_b2d.PROFILE_OVERLAP)
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
