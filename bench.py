@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--chunk-mb", type=int, default=None, help="staged exchange: wire MiB per pipeline chunk")
     ap.add_argument("--exch-ctas", type=int, default=None)
     ap.add_argument("--no-arena-buckets", action="store_true")
+    ap.add_argument("--optimizer-in-backward", action="store_true",
+                    help="apply the optimizer per DDP bucket right behind its allreduce (f-2; SGD / Adam / AdamW)")
     ap.add_argument("--cpu-batch", type=int, default=8)
     return ap.parse_args()
 
@@ -465,7 +467,7 @@ def run_b200(args):
     kw = dict(num_workers=world, use_gpu=True, b200_wire=args.wire, b200_algo=args.algo, b200_mem=args.mem,
               b200_timing=True, b200_max_ctas=args.max_ctas, b200_exch_ctas=args.exch_ctas,
               b200_chunk_bytes=(args.chunk_mb << 20) if args.chunk_mb else None,
-              b200_arena_buckets=not args.no_arena_buckets,
+              b200_arena_buckets=not args.no_arena_buckets, b200_optimizer_in_backward=args.optimizer_in_backward,
               # the product sizes its arena for the model alone; the evidence blocks of this file (isolated buckets,
               # parity cases, sweep up to 64 MiB of wire) stage extra buffers
               b200_arena_extra_bytes=(1 << 30) if world > 1 else 0)
@@ -651,6 +653,7 @@ def run_b200(args):
                        "l2_policy": "inputs larger than L2 (activations + 97.5 MiB of gradients per step >> 126 MB)",
                        "algo": args.algo, "algo_used": last_algo, "mem": args.mem, "nvls_bound": bool(getattr(comm, "nvls", False)),
                        "arena_buckets": bool(getattr(strategy, "b200_arena_buckets_active", False)),
+                       "optimizer_in_backward": bool(args.optimizer_in_backward),
                        "strategy": args.strategy, "hook": args.hook},
             "e2e": {"value": round(e2e_value, 2), "unit": unit + "/sec", "ms_per_step": round(e2e_ms / args.steps, 3),
                     "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)) * world,

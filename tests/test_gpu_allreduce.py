@@ -375,12 +375,12 @@ def test_nvls_matches_the_exact_sum_to_one_rounding(algo):
 def test_auto_prefers_nvls_from_four_ranks_up():
     from ray_lightning_b200 import _b2d
     g = _nvls_group()
-    a = g.ranks[0].ctx.plan(8 << 20, _b2d.WIRE_BF16)[0]
+    a = g.ranks[0].ctx.plan(32 << 20, _b2d.WIRE_BF16)[0]        # 64 MiB of wire: above every one-shot range
     assert a == (_b2d.ALGO_NVLS if g.world >= 4 else _b2d.ALGO_STAGED)
     for rk in g.ranks:
         rk.ctx.set_nvls_auto(False)
     try:
-        assert g.ranks[0].ctx.plan(8 << 20, _b2d.WIRE_BF16)[0] == _b2d.ALGO_STAGED
+        assert g.ranks[0].ctx.plan(32 << 20, _b2d.WIRE_BF16)[0] == _b2d.ALGO_STAGED
     finally:
         for rk in g.ranks:
             rk.ctx.set_nvls_auto(True)
