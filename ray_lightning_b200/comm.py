@@ -487,8 +487,9 @@ class InBackwardOptimizer(torch.optim.Optimizer):
         st = self._pstate.get(id(p))
         if st is None:
             g = self.param_groups[0]
-            s1 = torch.zeros_like(p, memory_format=torch.contiguous_format) if (self.kind == 1 or g.get("momentum", 0) != 0) else None
-            s2 = torch.zeros_like(p, memory_format=torch.contiguous_format) if self.kind == 1 else None
+            # preserve_format: the state's memory order is the parameter's (channels_last weights stay channels_last)
+            s1 = torch.zeros_like(p) if (self.kind == 1 or g.get("momentum", 0) != 0) else None
+            s2 = torch.zeros_like(p) if self.kind == 1 else None
             st = self._pstate[id(p)] = (s1, s2)
         return st
 
@@ -498,8 +499,13 @@ class InBackwardOptimizer(torch.optim.Optimizer):
         sig = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(params, grads))
         idx = bucket.index()
         if self._tables.get(idx) != sig:
-            if any(p.dtype != torch.float32 or not p.is_contiguous() for p in params):
-                raise ValueError("optimizer-in-backward needs contiguous fp32 parameters")
+            # the kernel walks parameter, gradient and state in MEMORY order: they must be dense and share one layout
+            # (DDP lays a bucket's gradient views out with the parameter's own strides, reducer.cpp initialize_bucket_views)
+            for p_, g_ in zip(params, grads):
+                dense = p_.is_contiguous() or (p_.dim() == 4 and p_.is_contiguous(memory_format=torch.channels_last)) or \
+                    (p_.dim() == 5 and p_.is_contiguous(memory_format=torch.channels_last_3d))
+                if p_.dtype != torch.float32 or not dense or g_.stride() != p_.stride():
+                    raise ValueError("optimizer-in-backward needs dense fp32 parameters whose gradient views share their layout")
             offs = [(g.data_ptr() - buf.data_ptr()) // 4 for g in grads]
             st = [self._states(p) for p in params]
             comm.ctx.optim_register(idx, [p.data_ptr() for p in params],

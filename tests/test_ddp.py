@@ -110,6 +110,26 @@ def test_custom_resources_and_overrides(ray_start_4_cpus_extra):
     assert ray.available_resources().get("extra") == 4.0
 
 
+def test_default_contract_is_the_references_and_bf16_is_asked_for_the_references_way():
+    """No hook given -> DDP's default arithmetic (divide, fp32 SUM), like the reference (ray_lightning/ray_ddp.py:75,112-116
+    registers none).  `ddp_comm_hook=bf16_compress_hook` — how one asks the reference for bf16 compression — selects the
+    fused bf16-wire path instead of torch's cast + allreduce + copy sequence."""
+    from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+    s = RayStrategy(num_workers=2, use_gpu=True)
+    assert s._ddp_comm_hook.__name__ == "b200_allreduce_hook" and s._ddp_comm_state.wire == "fp32"
+    assert s._ddp_comm_state.arena_buckets                       # fp32: DDP's buckets go into the arena
+    b = RayStrategy(num_workers=2, use_gpu=True, ddp_comm_hook=default_hooks.bf16_compress_hook)
+    assert b._ddp_comm_hook.__name__ == "b200_allreduce_hook" and b._ddp_comm_state.wire == "bf16"
+    assert not b._ddp_comm_state.arena_buckets
+    # with a wrapper around it the user's composition is left alone
+    w = RayStrategy(num_workers=2, use_gpu=True, ddp_comm_hook=default_hooks.bf16_compress_hook,
+                    ddp_comm_wrapper=default_hooks.fp16_compress_wrapper)
+    assert w._ddp_comm_hook is default_hooks.bf16_compress_hook
+    # and on CPU workers nothing is injected at all
+    c = RayStrategy(num_workers=2, use_gpu=False)
+    assert c._ddp_comm_hook is None
+
+
 def test_strategy_is_picklable_and_kwargs_pass_through():
     import cloudpickle
     s = RayStrategy(num_workers=2, use_gpu=True, bucket_cap_mb=5, find_unused_parameters=False,
