@@ -613,16 +613,11 @@ def b200_buffer_hook(state: ArenaBufferSync, buffers):
 
 
 def _pg_timeout_ms(group=None):
-    """Timeout of the control-plane process group in ms (None: keep the library default of 10 minutes)."""
+    """What torch's own collectives of this process group's backend wait before giving up (10 min for NCCL, 30 for gloo;
+    torch exposes no getter for a group's individual timeout) — in ms; None keeps the library default of 10 minutes."""
     try:
-        pg = group if group is not None else dist.distributed_c10d._get_default_group()
-        t = dist.distributed_c10d._get_default_timeout(dist.get_backend(pg)) if not hasattr(pg, "options") else None
-        opt = getattr(pg, "options", None)
-        to = getattr(opt, "_timeout", None) if opt is not None else t
-        if to is None:
-            to = t
-        ms = int(to.total_seconds() * 1000)
-        return max(ms, 60_000)
+        backend = dist.get_backend(group)
+        return max(int(dist.distributed_c10d._get_default_timeout(backend).total_seconds() * 1000), 60_000)
     except Exception:
         return None
 

@@ -167,7 +167,9 @@ __device__ __forceinline__ uint4 scale_f32x4(const uint4& v, float s) {
 }
 
 template <int W, bool BF16, bool NVLS, bool INPLACE>
-__global__ void __launch_bounds__(kExThreads, 2) exch_kernel(const __grid_constant__ ExParams P) {
+// NVLS keeps only U results in registers (64 registers -> a quarter of an SM's register file per CTA, 4 CTAs/SM); the
+// P2P variant holds W copies per pack (<= 128 registers, 2 CTAs/SM).
+__global__ void __launch_bounds__(kExThreads, NVLS ? 4 : 2) exch_kernel(const __grid_constant__ ExParams P) {
   static_assert(!(INPLACE && BF16), "in-place exchange exists for the fp32 wire only");
   constexpr int WW = W > 0 ? W : B2D_MAX_WORLD;
   const int world = W > 0 ? W : P.world;

@@ -326,8 +326,6 @@ class ShardedOptimizer(torch.optim.Optimizer):
                     box = first if first is not None else torch.tensor(float(self._steps))
                     for i in range(len(sh.params)):
                         state.setdefault(self._sd_index[i], {})[key] = box.clone() if isinstance(box, torch.Tensor) else box
-            if not keys and self._steps > 0:
-                pass
         return {"state": state, "param_groups": pgs}
 
     def state_dict(self):
