@@ -323,6 +323,27 @@ int emu_adam_push(void* h, int nvls, size_t param_off, float** m, float** v, flo
   return bad.load() ? -1 : 0;
 }
 
+// K14: one optimizer step of a bucket whose parameters (and their state tensors) are separate allocations.
+int emu_bucket_optim(float** params, float** state1, float** state2, const unsigned* seg_start, int nseg, const float* grads,
+                     size_t n, int kind, float lr, float momentum, float wd, float beta1, float beta2, float eps, int step, int adamw) {
+  OptimParams P{};
+  P.param_ptr = params; P.state1_ptr = state1; P.state2_ptr = state2; P.seg_start = seg_start; P.nseg = nseg;
+  P.grads = grads; P.n = n; P.kind = kind; P.lr = lr; P.momentum = momentum; P.weight_decay = wd;
+  if (kind == 1) {
+    AdamConsts& a = P.adam;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = wd;
+    a.one_minus_beta1 = static_cast<float>(1.0 - static_cast<double>(beta1));
+    a.one_minus_beta2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+    double b1p = 1.0, b2p = 1.0;
+    for (int i = 0; i < step; ++i) { b1p *= static_cast<double>(beta1); b2p *= static_cast<double>(beta2); }
+    a.step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - b1p));
+    a.inv_bc2_sqrt = 1.0f / static_cast<float>(std::sqrt(1.0 - b2p));
+    a.decay_mul = static_cast<float>(1.0 - static_cast<double>(lr) * static_cast<double>(wd));
+    a.adamw = adamw;
+  }
+  return launch_one(2, kStThreads, [P] { bucket_optim_kernel(P); });
+}
+
 // bufs[r]: rank r's fp32 bucket, reduced in place.  algo: 1 one-shot, 2 two-shot, 3 two-shot NVLS (fused).
 // parity selects the half of the (single) double-buffered slot, exactly like get_slot() in b2d.cu.
 int emu_allreduce(void* h, int algo, int bf16, float** bufs, size_t n, float scale, int grid, int parity, int use_generic_w,

@@ -43,6 +43,9 @@ def emu(tmp_path_factory):
     lib.emu_adam_push.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(FP), ctypes.POINTER(FP), ctypes.POINTER(FP),
                                   ctypes.c_size_t, LP, ctypes.c_int, LP, LP, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                   ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_int]
+    lib.emu_bucket_optim.argtypes = [ctypes.POINTER(FP), ctypes.POINTER(FP), ctypes.POINTER(FP), UP, ctypes.c_int, FP, ctypes.c_size_t,
+                                     ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                     ctypes.c_float, ctypes.c_int, ctypes.c_int]
     lib.emu_k0.argtypes = [FP, ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_int]
     lib.emu_sharded_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(FP), ctypes.c_size_t, ctypes.POINTER(FP),
                                      ctypes.POINTER(FP), ctypes.c_size_t, ctypes.POINTER(ctypes.c_longlong), ctypes.c_float,
@@ -383,3 +386,41 @@ def test_reduce_to_owner_and_adam_push_on_cpu_threads(emu, world, generic, bf16,
             np.testing.assert_allclose(views[0], ref.detach().numpy(), rtol=2e-5, atol=2e-6)
     finally:
         emu.emu_group_destroy(g)
+
+
+@pytest.mark.parametrize("opt_name", ["sgd", "sgd_plain", "adam", "adamw"])
+def test_bucket_optimizer_kernel_on_cpu_threads(emu, opt_name):
+    """K14 (optimizer step of one DDP bucket, parameters in separate allocations of odd sizes) against torch.optim over
+    three steps."""
+    sizes = [5, 1, 37, 1000, 3]
+    torch.manual_seed(3)
+    ref = [torch.nn.Parameter(torch.randn(n)) for n in sizes]
+    mk = {"sgd": lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-2),
+          "sgd_plain": lambda ps: torch.optim.SGD(ps, lr=0.05),
+          "adam": lambda ps: torch.optim.Adam(ps, lr=1e-2, weight_decay=1e-2),
+          "adamw": lambda ps: torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.05)}[opt_name]
+    opt = mk(ref)
+    params = [p.detach().numpy().copy() for p in ref]
+    s1 = [np.zeros(n, np.float32) for n in sizes]
+    s2 = [np.zeros(n, np.float32) for n in sizes]
+    start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    g = opt.param_groups[0]
+    for step in (1, 2, 3):
+        grads = torch.randn(sum(sizes), generator=torch.Generator().manual_seed(step)) * 0.1
+        off = 0
+        for p, n in zip(ref, sizes):
+            p.grad = grads[off:off + n].clone()
+            off += n
+        opt.step()
+        gb = grads.numpy().copy()
+        kind = 0 if opt_name.startswith("sgd") else 1
+        betas = g.get("betas", (0.0, 0.0))
+        rc = emu.emu_bucket_optim(ptrs(params), ptrs(s1), ptrs(s2), start.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), len(sizes),
+                                  gb.ctypes.data_as(FP), sum(sizes), kind, g["lr"], g.get("momentum", 0.0), g["weight_decay"],
+                                  betas[0], betas[1], g.get("eps", 0.0), step, int(opt_name == "adamw"))
+        assert rc == 0
+        for mine, p in zip(params, ref):
+            np.testing.assert_allclose(mine, p.detach().numpy(), rtol=2e-5, atol=2e-6)
+    if opt_name == "sgd":
+        for mine, p in zip(s1, ref):
+            np.testing.assert_allclose(mine, opt.state[p]["momentum_buffer"].numpy(), rtol=2e-5, atol=2e-6)
