@@ -300,7 +300,9 @@ int b2d_arena_reset(b2d_ctx* ctx);
  * initialize_buckets), reached from ray_lightning/ray_ddp.py:75,112-116 with gradient_as_bucket_view=True.
  * b2d_pool_alloc / b2d_pool_free have the signature torch.cuda.memory.CUDAPluggableAllocator expects; while a
  * context is bound (b2d_pool_bind; NULL unbinds) allocations of its device are bump-allocated from its
- * symmetric arena.  A bucket that lives there is exchanged IN PLACE by the fp32-wire staged algorithms. */
+ * symmetric arena; what the arena cannot take is served by cudaMalloc (and freed again), so torch never sees an
+ * out-of-memory from this pool.  A bucket that lives in the arena is exchanged IN PLACE by the fp32-wire staged
+ * algorithms; one that does not is staged like any other tensor. */
 int b2d_pool_bind(b2d_ctx* ctx);
 void* b2d_pool_alloc(size_t size, int device, void* stream);
 void b2d_pool_free(void* ptr, size_t size, int device, void* stream);

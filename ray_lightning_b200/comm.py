@@ -43,9 +43,13 @@ def arena_bytes_for(total_grad_elems, extra_bytes=0, wire="fp32", arena_buckets=
                   iteration (reducer.hpp:125-151) and the regions of the old layout are recycled (first fit), so
                   6 B/element covers the transient;
       fp32 wire : the same at 4 B/element -> 12 B/element — or, when DDP's bucket tensors themselves live in the
-                  arena (exchanged in place, no staging), the two generations of bucket storage: 10 B/element;
+                  arena (exchanged in place, no staging): the two generations of bucket storage, 8 B/element, plus
+                  256 MiB for the one coalescing buffer DDP's initial parameter broadcast allocates under the same
+                  pool (torch caches and re-uses it; anything the arena cannot take falls back to cudaMalloc);
     plus 64 MiB for the signal pad, alignment and small buckets."""
-    per = 6 if wire == "bf16" else (10 if arena_buckets else 12)
+    if wire != "bf16" and arena_buckets:
+        return int(8 * total_grad_elems + (320 << 20) + extra_bytes)
+    per = 6 if wire == "bf16" else 12
     return int(per * total_grad_elems + (64 << 20) + extra_bytes)
 
 

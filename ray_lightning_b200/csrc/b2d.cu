@@ -1864,15 +1864,29 @@ int b2d_pool_bind(b2d_ctx* ctx) {
   return B2D_OK;
 }
 
+// Allocations the arena could not take (exhausted, or no context bound): ordinary device memory, so torch sees no
+// out-of-memory.  A bucket that ends up there is simply not exchanged in place (the hook stages it like any tensor).
+static std::map<void*, size_t> g_pool_plain;
+
 void* b2d_pool_alloc(size_t size, int device, void* stream) {
   (void)stream;
   b2d_ctx* ctx;
   { std::lock_guard<std::mutex> lk(g_pool_mu); ctx = g_pool_ctx; }
-  if (ctx == nullptr || ctx->device != device) return nullptr;
   void* p = nullptr;
-  size_t off = 0;
-  if (b2d_arena_alloc(ctx, size, &p, &off) != B2D_OK) return nullptr;
-  {
+  size_t off = ~static_cast<size_t>(0);
+  if (ctx != nullptr && ctx->device == device && b2d_arena_alloc(ctx, size, &p, &off) != B2D_OK) p = nullptr;
+  if (p == nullptr) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device);
+    if (cudaMalloc(&p, size) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (p == nullptr) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool_plain[p] = size;
+    off = ~static_cast<size_t>(0);
+  }
+  if (ctx != nullptr) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->pool_allocs += 1;
     for (uint64_t v : {static_cast<uint64_t>(off), static_cast<uint64_t>(size)})
@@ -1882,8 +1896,14 @@ void* b2d_pool_alloc(size_t size, int device, void* stream) {
 }
 
 void b2d_pool_free(void* ptr, size_t size, int device, void* stream) {
-  // arena memory lives as long as the context: bump-allocated, given back by b2d_arena_reset / destroy
-  (void)ptr; (void)size; (void)device; (void)stream;
+  (void)size; (void)device; (void)stream;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool_plain.find(ptr);
+    if (it == g_pool_plain.end()) return;   // arena memory lives as long as its context (bump-allocated)
+    g_pool_plain.erase(it);
+  }
+  cudaFree(ptr);
 }
 
 // ---- introspection -----------------------------------------------------------------------

@@ -51,7 +51,7 @@ def test_hook_state_sizing_and_pickling():
     from ray_lightning_b200.comm import B200HookState, arena_bytes_for
     assert arena_bytes_for(25557032) == 12 * 25557032 + (64 << 20)                                   # fp32 wire, staged
     assert arena_bytes_for(25557032, wire="bf16") == 6 * 25557032 + (64 << 20)
-    assert arena_bytes_for(25557032, wire="fp32", arena_buckets=True, extra_bytes=5) == 10 * 25557032 + (64 << 20) + 5
+    assert arena_bytes_for(25557032, wire="fp32", arena_buckets=True, extra_bytes=5) == 8 * 25557032 + (320 << 20) + 5
     st = B200HookState(wire="fp32", algo="two_shot", total_grad_elems=1000, max_ctas=32)
     st.calls, st.seen = 5, {0: 10}
     st2 = pickle.loads(pickle.dumps(st))
