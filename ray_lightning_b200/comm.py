@@ -503,13 +503,15 @@ class InBackwardOptimizer(torch.optim.Optimizer):
         sig = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(params, grads))
         idx = bucket.index()
         if self._tables.get(idx) != sig:
-            # the kernel walks parameter, gradient and state in MEMORY order: they must be dense and share one layout
-            # (DDP lays a bucket's gradient views out with the parameter's own strides, reducer.cpp initialize_bucket_views)
-            for p_, g_ in zip(params, grads):
+            # The kernel walks parameter, gradient and state in MEMORY order.  For a dense parameter the Reducer lays the
+            # bucket view out with the parameter's own strides (reducer.cpp initialize_bucket_views, the "gradient layout
+            # contract"), so memory order agrees — also for channels_last weights.  (GradBucket.gradients() re-views the same
+            # bytes as contiguous tensors of the parameter's sizes: only their data pointers are used here.)
+            for p_ in params:
                 dense = p_.is_contiguous() or (p_.dim() == 4 and p_.is_contiguous(memory_format=torch.channels_last)) or \
                     (p_.dim() == 5 and p_.is_contiguous(memory_format=torch.channels_last_3d))
-                if p_.dtype != torch.float32 or not dense or g_.stride() != p_.stride():
-                    raise ValueError("optimizer-in-backward needs dense fp32 parameters whose gradient views share their layout")
+                if p_.dtype != torch.float32 or not dense:
+                    raise ValueError("optimizer-in-backward needs dense (contiguous or channels_last) fp32 parameters")
             offs = [(g.data_ptr() - buf.data_ptr()) // 4 for g in grads]
             st = [self._states(p) for p in params]
             comm.ctx.optim_register(idx, [p.data_ptr() for p in params],

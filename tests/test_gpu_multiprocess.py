@@ -230,14 +230,21 @@ def _inbw_worker(rank, world, port, ret):
     dev = torch.device("cuda", rank % torch.cuda.device_count())
     torch.cuda.set_device(dev)
 
-    def make():
+    def make_mlp():
         torch.manual_seed(0)
         return nn.Sequential(nn.Linear(37, 531), nn.ReLU(), nn.Linear(531, 257), nn.ReLU(), nn.Linear(257, 11)).to(dev)
 
+    def make_conv():     # channels_last weights: parameter, gradient view and state share the NHWC memory order
+        torch.manual_seed(0)
+        m = nn.Sequential(nn.Unflatten(1, (1, 37, 1)), nn.Conv2d(1, 16, (3, 1)), nn.ReLU(), nn.Conv2d(16, 8, (3, 1)),
+                          nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(8, 11)).to(dev)
+        return m.to(memory_format=torch.channels_last)
+
     ok, info, states = True, {}, []
     try:
-        for name, mk in (("sgd", lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-2)),
-                         ("adamw", lambda ps: torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.05))):
+        for name, mk, make in (("sgd", lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-2), make_mlp),
+                               ("adamw", lambda ps: torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.05), make_mlp),
+                               ("sgd_nhwc", lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9), make_conv)):
             kw = dict(device_ids=[dev.index], bucket_cap_mb=0.25, gradient_as_bucket_view=True)
             ours, stock = DDP(make(), **kw), DDP(make(), **kw)
             st = B200HookState(wire="fp32", total_grad_elems=sum(p.numel() for p in stock.parameters()), mem="ipc")
