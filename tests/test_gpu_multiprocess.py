@@ -234,11 +234,20 @@ def _inbw_worker(rank, world, port, ret):
         torch.manual_seed(0)
         return nn.Sequential(nn.Linear(37, 531), nn.ReLU(), nn.Linear(531, 257), nn.ReLU(), nn.Linear(257, 11)).to(dev)
 
+    class Conv(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1, self.c2, self.fc = nn.Conv2d(4, 16, 3, padding=1), nn.Conv2d(16, 8, 3, padding=1), nn.Linear(8, 11)
+
+        def forward(self, x):
+            x = x[:, :36].reshape(-1, 4, 3, 3).contiguous(memory_format=torch.channels_last)
+            return self.fc(torch.relu(self.c2(torch.relu(self.c1(x)))).mean(dim=(2, 3)))
+
     def make_conv():     # channels_last weights: parameter, gradient view and state share the NHWC memory order
         torch.manual_seed(0)
-        m = nn.Sequential(nn.Unflatten(1, (1, 37, 1)), nn.Conv2d(1, 16, (3, 1)), nn.ReLU(), nn.Conv2d(16, 8, (3, 1)),
-                          nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(8, 11)).to(dev)
-        return m.to(memory_format=torch.channels_last)
+        m = Conv().to(dev).to(memory_format=torch.channels_last)
+        assert not m.c1.weight.is_contiguous() and m.c1.weight.is_contiguous(memory_format=torch.channels_last)
+        return m
 
     ok, info, states = True, {}, []
     try:
@@ -291,4 +300,4 @@ def test_optimizer_in_backward_matches_stock_ddp_plus_optimizer():
     for r in range(2):
         assert ret[r]["ok"], dict(ret[r])
         # one bucket in the first iteration, two after DDP's re-layout
-        assert ret[r]["sgd"]["applied"] >= 6 and ret[r]["adamw"]["applied"] >= 6
+        assert ret[r]["sgd"]["applied"] >= 6 and ret[r]["adamw"]["applied"] >= 6 and ret[r]["sgd_nhwc"]["applied"] >= 6
