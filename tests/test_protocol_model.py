@@ -288,3 +288,99 @@ def test_staged_exchange_single_buffered_is_safe_too():
 def test_staged_model_catches_a_missing_reuse_edge():
     bad = explore_staged(2, 3, 1, reuse_edge=False)
     assert bad is not None and "holds" in bad
+
+
+def explore_owner(world, steps, buckets, step_fence=True, max_states=4_000_000):
+    """The sharded path (csrc/b2d_owner.cuh): per rank, per step k —
+        S  for every reduce bucket b: stage b into the bucket's SINGLE staging region; publish staged = idx
+        X  for every bucket: wait staged of ALL ranks; the owner side reads the bucket's staging region of every rank
+           (must hold step k); after the last bucket: push the own parameter shard into every rank (version k);
+           publish published = k + 1
+        U  wait published of ALL ranks; now every rank's copy of every shard must be version k (the step returns)
+    The staging regions have no double buffer: what fences their re-use is that S of step k+1 starts only after the rank's
+    own U of step k (host stream order: backward follows optimizer.step()).  Checked: every read sees the step it
+    expects, no deadlock; without that fence a violating schedule exists."""
+    idx = lambda k, b: k * buckets + b + 1
+    prog = {
+        "S": [x for k in range(steps) for b in range(buckets) for x in (("stage", (k, b)), ("pubA", idx(k, b)))],
+        "X": [x for k in range(steps)
+              for x in ([y for b in range(buckets) for y in (("waitA", idx(k, b)), ("reduce", (k, b)))] + [("push", k), ("pubB", k + 1)])],
+        "U": [x for k in range(steps) for x in (("waitB", k + 1), ("check", k))],
+    }
+    roles = ("S", "X", "U")
+    stage0 = tuple(tuple([-1] * buckets) for _ in range(world))          # stage[rank][bucket] = step staged
+    par0 = tuple(tuple([-1] * world) for _ in range(world))              # par[rank][owner] = version of owner's shard held by rank
+    zero = tuple(tuple([0] * world) for _ in range(world))
+    init = (tuple((0, 0, 0) for _ in range(world)), stage0, par0, zero, zero)
+    seen, todo = {init}, deque([init])
+    while todo:
+        pcs, stage, par, cntA, cntB = todo.popleft()
+        moved, done_all = False, True
+        for r in range(world):
+            for ri, role in enumerate(roles):
+                pc = pcs[r][ri]
+                if pc == len(prog[role]):
+                    continue
+                done_all = False
+                op, arg = prog[role][pc]
+                nstage, npar, nA, nB = stage, par, cntA, cntB
+                if op == "stage":
+                    k, b = arg
+                    if step_fence and k >= 1 and pcs[r][2] < 2 * k:
+                        continue          # backward of step k starts after optimizer.step() of step k-1 has returned
+                    st = [list(x) for x in stage]
+                    st[r][b] = k
+                    nstage = tuple(tuple(x) for x in st)
+                elif op == "pubA":
+                    a = [list(x) for x in cntA]
+                    for p in range(world):
+                        a[p][r] = arg
+                    nA = tuple(tuple(x) for x in a)
+                elif op == "pubB":
+                    bb = [list(x) for x in cntB]
+                    for p in range(world):
+                        bb[p][r] = arg
+                    nB = tuple(tuple(x) for x in bb)
+                elif op == "waitA":
+                    if any(cntA[r][p] < arg for p in range(world)):
+                        continue
+                elif op == "waitB":
+                    if any(cntB[r][p] < arg for p in range(world)):
+                        continue
+                elif op == "reduce":
+                    k, b = arg
+                    for p in range(world):
+                        if stage[p][b] != k:
+                            return "rank %d reduces bucket %d of step %d but rank %d staged step %r" % (r, b, k, p, stage[p][b])
+                elif op == "push":
+                    pr = [list(x) for x in par]
+                    for p in range(world):
+                        pr[p][r] = arg
+                    npar = tuple(tuple(x) for x in pr)
+                elif op == "check":
+                    for o in range(world):
+                        if par[r][o] != arg:
+                            return "rank %d leaves step %d holding parameter version %r of owner %d" % (r, arg, par[r][o], o)
+                moved = True
+                row = list(pcs[r]); row[ri] = pc + 1
+                nxt = (pcs[:r] + (tuple(row),) + pcs[r + 1:], nstage, npar, nA, nB)
+                if nxt not in seen:
+                    seen.add(nxt)
+                    if len(seen) > max_states:
+                        raise RuntimeError("state space larger than expected")
+                    todo.append(nxt)
+        if not moved and not done_all:
+            return "deadlock at pcs %r" % (pcs,)
+    return None
+
+
+@pytest.mark.parametrize("world,steps,buckets", [(2, 3, 2), (3, 2, 2), (2, 4, 1)])
+def test_owner_path_protocol_is_safe(world, steps, buckets):
+    assert explore_owner(world, steps, buckets) is None
+
+
+def test_owner_model_catches_a_missing_step_fence():
+    """Single-buffered staging is only safe because backward k+1 follows optimizer.step() k: without it a fast rank
+    re-stages a bucket a slow owner has not reduced yet."""
+    bad = explore_owner(2, 2, 1, step_fence=False)
+    assert bad is not None and ("staged step" in bad or "parameter version" in bad)
