@@ -227,5 +227,62 @@ def ncu_loopback():
     g.close()
 
 
+def ncu_loopback_sharded():
+    """Single-GPU target for ncu: the sharded path's kernels (K11 seg_stage, K12 seg_reduce, K13 adam_push) on W loopback
+    ranks, one reduce bucket of 8.4 M elements made of 12 parameter segments, bf16 wire; then K14 (optimizer step of one
+    DDP bucket with parameters in separate allocations)."""
+    from ray_lightning_b200._b2d import AdamParams
+    world = int(os.environ.get("B2D_NCU_WORLD", "2"))
+    seg = 699_904                                   # 12 segments ~ one GPT-2-medium reduce bucket
+    nseg = 12
+    total = seg * nseg
+    g = LoopbackGroup(world, 0, arena_bytes=1 << 30, timeout_ms=20000)
+    segs = [(i * seg, seg, i % world) for i in range(nseg)]
+    # a flat layout grouped by owner: owner r holds the segments with i % world == r, contiguously
+    order = sorted(range(nseg), key=lambda i: (i % world, i))
+    offs = {i: k * seg for k, i in enumerate(order)}
+    segs = [(offs[i], seg, i % world) for i in range(nseg)]
+    shard_off = [0]
+    for r in range(world):
+        shard_off.append(shard_off[-1] + seg * len([i for i in range(nseg) if i % world == r]))
+    g.register_bucket(0, segs, "bf16")
+    grads = [torch.randn(total, device="cuda") * 0.01 for _ in range(world)]
+    reduced = [torch.zeros(shard_off[r + 1] - shard_off[r], device="cuda") for r in range(world)]
+    params = []
+    for rk in g.ranks:
+        p = rk.arena_tensor(total)
+        p.normal_()
+        params.append(p)
+    ms = [torch.zeros_like(t) for t in reduced]
+    vs = [torch.zeros_like(t) for t in reduced]
+    flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    for it in range(3):
+        for gr in grads:
+            gr.normal_()
+        flush.add_(1.0)
+        torch.cuda.synchronize()
+        g.reduce_to_owner(0, grads, reduced, shard_off, zero_grads=True)
+        g.synchronize()
+        groups = [[(0, shard_off[r + 1] - shard_off[r], dict(lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=it + 1, adamw=0))]
+                  for r in range(world)]
+        flush.add_(1.0)
+        torch.cuda.synchronize()
+        g.adam_push_(params, ms, vs, reduced, shard_off, groups)
+        g.synchronize()
+    # K14
+    ctx = g.ranks[0].ctx
+    ps = [torch.randn(seg, device="cuda") for _ in range(nseg)]
+    s1 = [torch.zeros_like(p) for p in ps]
+    bucket = torch.randn(total, device="cuda") * 0.01
+    ctx.optim_register(5, [p.data_ptr() for p in ps], [t.data_ptr() for t in s1], None, [i * seg for i in range(nseg)], [seg] * nseg)
+    hp = AdamParams(lr=0.05, beta1=0.0, beta2=0.0, eps=0.0, weight_decay=0.0, step=1, adamw=0, zero_grads=0)
+    for it in range(3):
+        flush.add_(1.0)
+        torch.cuda.synchronize()
+        ctx.bucket_optim(5, bucket.data_ptr(), total, 0, hp, 0.9, torch.cuda.current_stream())
+        torch.cuda.synchronize()
+    g.close()
+
+
 if __name__ == "__main__":
-    {"k0": k0, "loopback": loopback, "sweep": sweep, "tune": tune, "ncu_target": ncu_target, "ncu_loopback": ncu_loopback}[sys.argv[1]]()
+    {"k0": k0, "loopback": loopback, "sweep": sweep, "tune": tune, "ncu_target": ncu_target, "ncu_loopback": ncu_loopback, "ncu_loopback_sharded": ncu_loopback_sharded}[sys.argv[1]]()
