@@ -23,7 +23,9 @@ class RayShardedStrategy(RayStrategy, DDPSpawnShardedStrategy):
 
     def __init__(self, *args, **kwargs):
         kwargs.setdefault("b200_enable", True)
-        kwargs.setdefault("b200_wire", "bf16")    # FairScale's reduce_fp16 analogue; fp32 with b200_wire="fp32"
+        # wire format of the reduce-to-owner: like PL's sharded plugin (reduce_fp16 only under 16-bit precision) fp32
+        # unless the trainer runs at 16-bit / bf16 precision; b200_wire="bf16" | "fp32" forces it
+        kwargs.setdefault("b200_wire", None)
         super().__init__(*args, **kwargs)
         self._shards = None
         self._sharded_ready = False
@@ -33,20 +35,21 @@ class RayShardedStrategy(RayStrategy, DDPSpawnShardedStrategy):
             if self.use_gpu:
                 raise RuntimeError("RayShardedStrategy(use_gpu=True) needs a CUDA device in the worker")
             return self._configure_cpu_reference()
-        # GPU: no DDP wrapper at all — gradients are reduced to their owners inside optimizer.step()
-        from .comm import Communicator, arena_bytes_for
+        # GPU: no DDP wrapper at all — autograd hooks send every reduce bucket to its owners while backward runs
+        from .comm import Communicator
         o = self._b200
         total = sum(p.numel() for p in self.lightning_module.parameters() if p.requires_grad)
         # flat fp32 parameters (4 B/element) + one single-buffered staging copy at wire width + a gather buffer for
         # consolidated checkpoints (4 B/element)
-        wire_w = 2 if (o["wire"] or "bf16") == "bf16" else 4
+        wire = o["wire"] or ("bf16" if str(getattr(self, "precision", 32)) in ("16", "bf16") else "fp32")
+        wire_w = 2 if wire == "bf16" else 4
         nbytes = o["arena_bytes"] or int((8 + wire_w) * total + (128 << 20) + o["arena_extra_bytes"])
         self._comm = Communicator(self.global_rank, self.world_size, self.root_device.index, nbytes, mem=o["mem"],
                                   timing=o["timing"], max_ctas=o["max_ctas"], nvls=o["nvls"], timeout_ms=o["timeout_ms"],
                                   exch_ctas=o["exch_ctas"])
         # the flat layout follows the optimizer's parameter groups: built in setup_optimizers, once they are known
         self.model = self.lightning_module
-        self._sharded_wire = "bf16" if o["wire"] is None else o["wire"]
+        self._sharded_wire = wire
         self._sharded_ready = True
 
     def _configure_cpu_reference(self):

@@ -25,11 +25,6 @@ import torch
 
 from .partition import flat_layout, partition_parameters
 
-try:  # the real binding; the host-logic tests run this module with a communicator double and no libb2d
-    from ._b2d import AdamParams
-except Exception:  # pragma: no cover
-    AdamParams = None
-
 
 class FlatShards:
     """Flat parameter / gradient buffers of one module, the owner table and the reduce buckets."""
