@@ -132,7 +132,8 @@ struct Slot {
   // event after which the half may be staged into again (its last write-back has finished)
   uint32_t op_epoch0 = 0;
   size_t op_stage_off = 0;
-  cudaEvent_t reuse_ev[2] = {nullptr, nullptr};
+  cudaEvent_t reuse_ev[2] = {nullptr, nullptr};   // recorded on the write-back stream; owned by the slot (never the shared ring:
+                                                  // a ring event may have been re-recorded on another stream by the time it is waited for)
 };
 
 uint64_t process_nonce() {
@@ -201,7 +202,7 @@ struct b2d_ctx {
   cudaStream_t s_stage = nullptr, s_xfer = nullptr, s_unstage = nullptr;
   std::vector<cudaEvent_t> ev_ring;
   size_t ev_ring_idx = 0;
-  cudaEvent_t last_unstage_ev = nullptr;
+  cudaEvent_t last_unstage_ev = nullptr;   // own event, re-recorded after every write-back / parameter wait
   uint32_t epoch = 0;
   size_t chunk_bytes = 64u << 20;        // wire bytes per pipeline chunk (host launch cost grows with the chunk count)
   int exch_ctas = 64;                    // CTAs (256 threads) of the exchange kernel (the only one that waits for peers)
@@ -572,7 +573,6 @@ int get_slot(b2d_ctx* ctx, int key, size_t half_bytes, size_t n, int wire, int a
       }
       s.off = off;
       s.half = half_bytes;
-      s.reuse_ev[0] = s.reuse_ev[1] = nullptr;
     }
     s.n = n; s.wire = wire; s.algo = algo; s.grid = grid;
   }
@@ -843,8 +843,12 @@ int launch_staged(b2d_ctx* ctx, int key, float* grad, size_t n, int wire, float 
     cudaEvent_t ed = next_event(ctx);
     B2D_CUDA(ctx, cudaEventRecord(ed, ctx->s_unstage));
     B2D_CUDA(ctx, cudaStreamWaitEvent(comm, ed, 0));
-    ctx->last_unstage_ev = ed;
-    if (!inplace) slot->reuse_ev[half] = ed;
+    if (ctx->last_unstage_ev == nullptr) B2D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->last_unstage_ev, cudaEventDisableTiming));
+    B2D_CUDA(ctx, cudaEventRecord(ctx->last_unstage_ev, ctx->s_unstage));
+    if (!inplace) {
+      if (slot->reuse_ev[half] == nullptr) B2D_CUDA(ctx, cudaEventCreateWithFlags(&slot->reuse_ev[half], cudaEventDisableTiming));
+      B2D_CUDA(ctx, cudaEventRecord(slot->reuse_ev[half], ctx->s_unstage));
+    }
     slot->op_epoch0 = 0;
   }
   cudaError_t e = cudaGetLastError();
@@ -1154,6 +1158,8 @@ int b2d_ctx_destroy(b2d_ctx* ctx) {
     for (auto& kv : ctx->owner_buckets) { cudaFree(kv.second.d_flat_off); cudaFree(kv.second.d_start); }
     for (auto& kv : ctx->optim_buckets) { cudaFree(kv.second.d_ptr); cudaFree(kv.second.d_start); }
     for (auto& e : ctx->ev_ring) if (e != nullptr) cudaEventDestroy(e);
+    if (ctx->last_unstage_ev != nullptr) cudaEventDestroy(ctx->last_unstage_ev);
+    for (auto& kv : ctx->slots) for (cudaEvent_t e : kv.second.reuse_ev) if (e != nullptr) cudaEventDestroy(e);
     for (cudaStream_t st : {ctx->s_stage, ctx->s_xfer, ctx->s_unstage}) if (st != nullptr) cudaStreamDestroy(st);
     if (ctx->peers.mc_arena != nullptr) vmm_unmap(ctx->peers.mc_arena, ctx->arena_bytes);
     if (ctx->mc_handle != 0) {
@@ -1710,7 +1716,8 @@ int b2d_adam_push(b2d_ctx* ctx, float* params, float* exp_avg, float* exp_avg_sq
     cudaEvent_t ed = next_event(ctx);
     B2D_CUDA(ctx, cudaEventRecord(ed, ctx->s_unstage));
     B2D_CUDA(ctx, cudaStreamWaitEvent(comm, ed, 0));
-    ctx->last_unstage_ev = ed;
+    if (ctx->last_unstage_ev == nullptr) B2D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->last_unstage_ev, cudaEventDisableTiming));
+    B2D_CUDA(ctx, cudaEventRecord(ctx->last_unstage_ev, ctx->s_unstage));
     ctx->push_epoch = 0;
   }
   cudaError_t e = cudaGetLastError();
@@ -1809,6 +1816,7 @@ int b2d_arena_alloc(b2d_ctx* ctx, size_t bytes, void** dev_ptr, size_t* offset) 
 int b2d_arena_reset(b2d_ctx* ctx) {
   if (ctx == nullptr) return fail(nullptr, B2D_ERR_INVALID, "ctx is NULL");
   std::lock_guard<std::mutex> lk(ctx->mu);
+  for (auto& kv : ctx->slots) for (cudaEvent_t e : kv.second.reuse_ev) if (e != nullptr) cudaEventDestroy(e);
   ctx->slots.clear();
   ctx->slot_free.clear();
   ctx->slot_top = kSignalBytes;
