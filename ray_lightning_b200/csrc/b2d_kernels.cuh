@@ -19,6 +19,11 @@ namespace b2d {
 
 constexpr int kThreads = 512;
 constexpr int kMaxLoadsInFlight = 16;  // 16-byte loads per thread per batch
+// packs a thread handles per batch when every pack costs `per_pack` loads (W peer copies, or W x 2 gradient loads);
+// the generic-world instantiation (W = 0) takes one pack at a time
+constexpr int packs_per_batch(int per_pack) {
+  return per_pack > 0 && kMaxLoadsInFlight / (per_pack > 0 ? per_pack : 1) > 1 ? kMaxLoadsInFlight / (per_pack > 0 ? per_pack : 1) : 1;
+}
 
 constexpr int kTraceSlots = 8;  // globaltimer stamps per block: start, after each phase / barrier
 
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) k1_one_shot_kernel(const __grid_c
   trace_stamp(P.trace, 2);
 
   constexpr int WW = W > 0 ? W : B2D_MAX_WORLD;
-  constexpr int U = (W > 0 && kMaxLoadsInFlight / W > 1) ? kMaxLoadsInFlight / W : 1;
+  constexpr int U = packs_per_batch(W);
   for (size_t j = g; j < npacks; j += gt * U) {
     uint4 in[U][WW];
 #pragma unroll
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
   // UJ consecutive j per iteration so that 16 x 16-byte loads are in flight per thread
   {
     constexpr int LPP = BF16 ? 2 : 1;                       // 16-byte loads per pack
-    constexpr int UJ = (W > 0 && kMaxLoadsInFlight / (W * LPP) > 1) ? kMaxLoadsInFlight / (W * LPP) : 1;
+    constexpr int UJ = packs_per_batch(W * LPP);
     constexpr int B = WW * UJ;
     for (size_t j = g; j < slice; j += gt * UJ) {
       size_t p[B];
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
         }
       }
     } else {
-      constexpr int U = (W > 0 && kMaxLoadsInFlight / W > 1) ? kMaxLoadsInFlight / W : 1;
+      constexpr int U = packs_per_batch(W);
       for (size_t j = g; j < slice; j += gt * U) {
         uint4 in[U][WW];
 #pragma unroll
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) k2_two_shot_kernel(const __grid_c
     }
   }
   trace_stamp(P.trace, 3);
-  constexpr int UJ2 = (W > 0 && kMaxLoadsInFlight / W > 1) ? kMaxLoadsInFlight / W : 1;
+  constexpr int UJ2 = packs_per_batch(W);
   constexpr int B2 = WW * UJ2;
   // one gather pass over this block's packs of the slices in `mask` (16 loads in flight per thread)
   auto gather = [&](uint32_t mask) {

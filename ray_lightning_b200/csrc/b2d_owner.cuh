@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kExThreads, 2) seg_reduce_kernel(const __grid_
   const size_t cnt = q1 - q0;
   const size_t gt = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  constexpr int U = NVLS ? 8 : ((W > 0 && kMaxLoadsInFlight / W > 1) ? kMaxLoadsInFlight / W : 1);
+  constexpr int U = NVLS ? 8 : packs_per_batch(W);
   for (size_t j = g; j < cnt; j += gt * U) {
     uint4 in[U][NVLS ? 1 : WW];
 #pragma unroll

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kExThreads, NVLS ? 4 : 2) exch_kernel(const __
       }
     }
   } else {
-    constexpr int U = (W > 0 && kMaxLoadsInFlight / W > 1) ? kMaxLoadsInFlight / W : 1;
+    constexpr int U = packs_per_batch(W);
     for (size_t j = g; j < full; j += gt * U) {
       uint4 in[U][WW];
 #pragma unroll
