@@ -21,7 +21,7 @@ constexpr int kThreads = 512;
 constexpr int kMaxLoadsInFlight = 16;  // 16-byte loads per thread per batch
 // packs a thread handles per batch when every pack costs `per_pack` loads (W peer copies, or W x 2 gradient loads);
 // the generic-world instantiation (W = 0) takes one pack at a time
-constexpr int packs_per_batch(int per_pack) {
+__host__ __device__ constexpr int packs_per_batch(int per_pack) {
   return per_pack > 0 && kMaxLoadsInFlight / (per_pack > 0 ? per_pack : 1) > 1 ? kMaxLoadsInFlight / (per_pack > 0 ? per_pack : 1) : 1;
 }
 
