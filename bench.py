@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec, ResNet-50 RayStrategy (+ allreduce bus GB/s)"
 NVLINK_NOMINAL_GBS = 900.0    # NVLink 5, per direction per GPU
+EVIDENCE_TIMEOUT_S = 420     # link probe + parity + sweep + CPU baseline normally take about a minute
 NVLINK_FALLBACK_GBS = 770.0   # /opt/skills/guides/B200_PROFILING.md: measured peer copy — used only if the in-run probe fails
 
 
@@ -583,23 +584,12 @@ def run_b200(args):
             isolated.append((idx, n, float(t)))
         barrier()
 
-    link = parity = sweep = None
-    if world > 1 and comm is not None and args.hook == "b200":
-        link = link_probe(comm, dist, torch, world, rank)
-        if not args.no_parity:
-            try:
-                parity = parity_block(comm, dist, torch, world, rank, dev,
-                                      sorted(state.seen.values()) if state is not None and state.seen else [])
-            except Exception as e:
-                parity = {"all_ok": False, "error": repr(e)[:300]}
-        if not args.no_sweep:
-            try:
-                sweep = allreduce_sweep(comm, dist, torch, world, rank, [64 << 10, 1 << 20, 16 << 20, 64 << 20])
-            except Exception as e:
-                sweep = [{"error": repr(e)[:300]}]
-        barrier()
+    kernel_ms0, timed_launches0 = kernel_ms, timed_launches
 
-    if rank == 0:
+    def emit(link, parity, sweep, with_cpu):
+        """Rank 0: build and print THE json line (called once: normally after the evidence blocks, or by the
+        watchdog below if those hang)."""
+        kernel_ms, timed_launches = kernel_ms0, timed_launches0
         peaks, peak_src = measured_peaks()
         ms_per_step = total_ms / args.steps
         value = world * B / (ms_per_step / 1e3)
@@ -690,7 +680,7 @@ def run_b200(args):
         line["nvlink"] = link
         line["parity"] = parity
         line["allreduce_sweep"] = sweep
-        if not args.no_cpu_baseline and args.model.startswith("resnet"):
+        if with_cpu and not args.no_cpu_baseline and args.model.startswith("resnet"):
             try:
                 cb = cpu_reference(1, args.cpu_batch, 2, 1, args.model)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -698,6 +688,40 @@ def run_b200(args):
                 line["cpu_baseline"] = {"value": None, "unit": "images/sec", "cores": None, "kind": "reference",
                                         "sample": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
+
+    # Everything below is evidence AROUND the measurement (link probe, parity block, sweep, CPU baseline).  It contains
+    # collectives; should one of them ever hang, a watchdog still prints the bench line (without that evidence) and ends
+    # the process cleanly instead of leaving the driver without a number.
+    def _watchdog():      # a thread: the main thread may be blocked inside a CUDA / NCCL call, where no signal handler runs
+        if rank == 0:
+            emit(None, {"all_ok": False, "error": "evidence blocks timed out after %d s" % EVIDENCE_TIMEOUT_S}, None, False)
+        os._exit(0)
+
+    guard = None
+    if world > 1:
+        guard = threading.Timer(EVIDENCE_TIMEOUT_S, _watchdog)
+        guard.daemon = True
+        guard.start()
+    link = parity = sweep = None
+    if world > 1 and comm is not None and args.hook == "b200":
+        link = link_probe(comm, dist, torch, world, rank)
+        if not args.no_parity:
+            try:
+                parity = parity_block(comm, dist, torch, world, rank, dev,
+                                      sorted(state.seen.values()) if state is not None and state.seen else [])
+            except Exception as e:
+                parity = {"all_ok": False, "error": repr(e)[:300]}
+        if not args.no_sweep:
+            try:
+                sweep = allreduce_sweep(comm, dist, torch, world, rank, [64 << 10, 1 << 20, 16 << 20, 64 << 20])
+            except Exception as e:
+                sweep = [{"error": repr(e)[:300]}]
+        barrier()
+
+    if rank == 0:
+        emit(link, parity, sweep, True)
+    if guard is not None:
+        guard.cancel()
     barrier()
     strategy.teardown_worker()
 
