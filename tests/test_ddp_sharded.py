@@ -64,3 +64,28 @@ def test_test_without_fit(tmpdir, ray_start_2_cpus):
     trainer = get_trainer(tmpdir, strategy=RayShardedStrategy(num_workers=1))
     trainer.test(BoringModel())
     assert trainer.state.finished
+
+
+def test_flat_layout_keeps_shards_and_parameter_groups_contiguous():
+    """Integer contract of the group-aware flat layout (partition.flat_layout): every owner's shard is one contiguous,
+    8-aligned range; inside it every optimizer parameter group is one contiguous range; nothing overlaps; with a single
+    group the layout is the oracle's."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    for world in (1, 2, 3, 8):
+        numels = [int(x) for x in rng.integers(1, 5000, size=47)]
+        owner = partition_parameters(numels, world)
+        group_of = [int(x) for x in rng.integers(0, 3, size=len(numels))]
+        offs, shard_off, total = flat_layout(numels, owner, world, group_of=group_of)
+        assert shard_off[0] == 0 and shard_off[-1] == total and all(o % 8 == 0 for o in offs + shard_off)
+        spans = sorted((o, o + -(-n // 8) * 8) for o, n in zip(offs, numels))
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))             # no overlap
+        for r in range(world):
+            mine = [i for i in range(len(numels)) if owner[i] == r]
+            assert all(shard_off[r] <= offs[i] and offs[i] + numels[i] <= shard_off[r + 1] for i in mine)
+            seen = []
+            for i in sorted(mine, key=lambda i: offs[i]):
+                if not seen or seen[-1] != group_of[i]:
+                    seen.append(group_of[i])
+            assert len(seen) == len(set(seen))                                   # each group appears as ONE run
+        assert flat_layout(numels, owner, world, group_of=[0] * len(numels)) == ddp_oracle.shard_layout(numels, owner, world)

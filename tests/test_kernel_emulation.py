@@ -424,3 +424,56 @@ def test_bucket_optimizer_kernel_on_cpu_threads(emu, opt_name):
     if opt_name == "sgd":
         for mine, p in zip(s1, ref):
             np.testing.assert_allclose(mine, opt.state[p]["momentum_buffer"].numpy(), rtol=2e-5, atol=2e-6)
+
+
+def test_owner_path_with_ranks_that_own_nothing(emu):
+    """Edge cases of K12 / K13: a reduce bucket in which one rank owns no segment at all (empty staging range), and a
+    parameter push from a rank whose shard is empty — every other rank's result must be unaffected."""
+    world = 4
+    sig = emu.emu_signal_bytes()
+    g = emu.emu_group_create(world, 4 << 20)
+    try:
+        # three parameters, owners 0, 1 and 3: rank 2 owns nothing, in the bucket and in the flat space
+        numels = [504, 1000, 256]
+        owner = [0, 1, 3]
+        offs, cur = [], 0
+        shard_off = [0]
+        for r in range(world):
+            for i, n in enumerate(numels):
+                if owner[i] == r:
+                    offs.append((i, cur))
+                    cur += n
+            shard_off.append(cur)
+        offs = [o for _, o in sorted(offs)]
+        total = cur
+        segs = [(offs[i], numels[i], owner[i]) for i in range(3)]
+        flat, start, opack = _seg_table(segs, world, 4)
+        assert opack[2] == opack[3]                      # rank 2's range of the staging region is empty
+        per_rank = [torch.randn(total, generator=torch.Generator().manual_seed(r)) * 0.1 for r in range(world)]
+        grads = [t.numpy().copy() for t in per_rank]
+        n_own = [shard_off[r + 1] - shard_off[r] for r in range(world)]
+        reduced = [np.full(max(n, 8), 9.0, np.float32) for n in n_own]
+        off = (ctypes.c_longlong * (world + 1))(*shard_off)
+        scale = 0.25
+        rc = emu.emu_reduce_to_owner(g, 0, 0, ptrs(grads), ptrs(reduced), off, (ctypes.c_longlong * len(flat))(*flat),
+                                     (ctypes.c_uint * len(start))(*start), len(flat), (ctypes.c_uint * len(opack))(*opack),
+                                     sig + (1 << 20), scale, 1, 0, 1, 0, 0)
+        assert rc == 0
+        want = ddp_oracle.allreduce_fp32_wire(per_rank, scale).numpy()
+        for r in range(world):
+            assert same_bits(reduced[r][:n_own[r]], want[shard_off[r]:shard_off[r + 1]]), r
+        assert float(reduced[2][0]) == 9.0               # untouched
+        # push: every rank's copy of every shard becomes its owner's; rank 2 pushes nothing
+        poff = sig + (2 << 20)
+        views = []
+        for r in range(world):
+            v = np.ctypeslib.as_array(emu.emu_arena_ptr(g, r, poff), shape=(total,))
+            v[:] = -1.0
+            v[shard_off[r]:shard_off[r + 1]] = float(r + 1)
+            views.append(v)
+        assert emu.emu_adam_push(g, 0, poff, None, None, None, total, off, 0, None, None, 0, 0, 0, 0, 0, 1, 0, 2, 0, 0) == 0
+        for r in range(world):
+            for o in range(world):
+                assert (views[r][shard_off[o]:shard_off[o + 1]] == float(o + 1)).all(), (r, o)
+    finally:
+        emu.emu_group_destroy(g)
